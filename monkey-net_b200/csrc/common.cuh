@@ -1,0 +1,102 @@
+// Shared helpers for libmonkey_b200 (sm_100a).  No torch types anywhere in csrc/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MK_EXPORT extern "C" __attribute__((visibility("default")))
+// the public header declares the same symbols without the visibility attribute; re-declaring with it first keeps them exported
+
+void mk_set_error(const char* fmt, ...);
+int mk_check_launch(const char* what);
+
+#define MK_REQUIRE(cond, ...)            \
+    do {                                 \
+        if (!(cond)) {                   \
+            mk_set_error(__VA_ARGS__);   \
+            return -1;                   \
+        }                                \
+    } while (0)
+
+static inline int mk_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+static inline long long mk_cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ void fma4(float4& acc, float4 a, float s) {
+    acc.x = fmaf(a.x, s, acc.x); acc.y = fmaf(a.y, s, acc.y); acc.z = fmaf(a.z, s, acc.z); acc.w = fmaf(a.w, s, acc.w);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in every thread.  `red` needs NV*32 floats of smem.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[i * 32 + wid] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float t = (lane < nw) ? red[i * 32 + lane] : 0.f;
+        v[i] = warp_sum(t);
+    }
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float t = (lane < nw) ? red[lane] : -INFINITY;
+    return warp_max(t);
+}
+
+// reference coordinate grid (modules/util.py:26-42): x_j = 2*(j/(w-1)) - 1
+__device__ __forceinline__ float grid_coord(int j, int n) { return 2.f * ((float)j / (float)(n - 1)) - 1.f; }
+
+// nearest source index of F.interpolate(size=...) (ATen nearest_neighbor_compute_source_index)
+__device__ __forceinline__ int nearest_src(int dst, int in, int out) {
+    float scale = (float)in / (float)out;
+    int s = (int)floorf((float)dst * scale);
+    return s < in - 1 ? s : in - 1;
+}
+// linear source index, align_corners=False (ATen area_pixel_compute_source_index)
+__device__ __forceinline__ void linear_src(int dst, int in, int out, int& i0, int& i1, float& l1) {
+    float scale = (float)in / (float)out;
+    float s = scale * ((float)dst + 0.5f) - 0.5f;
+    s = s < 0.f ? 0.f : s;
+    i0 = (int)s;
+    if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+}

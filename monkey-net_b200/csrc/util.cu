@@ -1,0 +1,210 @@
+// Error plumbing + layout-edge kernels (NCDHW <-> NHWC, channel-slice copy/add).  HBM-bound, coalesced on the
+// NHWC side; the NCDHW side is the reference's API layout and is only touched at the module boundary.
+#include "common.cuh"
+#include "../../include/monkey_b200.h"
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void mk_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int mk_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        mk_set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+MK_EXPORT const char* mk_last_error(void) { return g_err; }
+MK_EXPORT int mk_version(void) { return 100; }
+
+MK_EXPORT int mk_fill_zero(void* ptr, long long bytes, void* stream) {
+    if (bytes <= 0) return 0;
+    cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        mk_set_error("mk_fill_zero: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ NCDHW -> NHWC
+// One thread per (output pixel, physical channel).  Reads are strided on the NCDHW side (the channel planes are
+// far apart); the tensors that cross this edge are images (C = 3) so the traffic is negligible next to the convs.
+__global__ void k_ncdhw_to_nhwc(const float* __restrict__ src, int C, int D, int Hd, int Wd, long long sb,
+                                long long sc, long long sd, long long sh, long long sw, int step,
+                                float* __restrict__ dst, int Cp, int ld, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % Cp);
+    long long p = i / Cp;
+    int w = (int)(p % Wd);
+    long long t = p / Wd;
+    int h = (int)(t % Hd);
+    long long n = t / Hd;
+    int d = (int)(n % D);
+    long long b = n / D;
+    float v = 0.f;
+    if (c < C) v = src[b * sb + c * sc + d * sd + (long long)h * step * sh + (long long)w * step * sw];
+    dst[p * ld + c] = v;
+}
+
+MK_EXPORT int mk_ncdhw_to_nhwc(const float* src, int B, int C, int D, int H, int W, long long sb, long long sc,
+                               long long sd, long long sh, long long sw, int step, float* dst, int Cp, int ld,
+                               void* stream) {
+    MK_REQUIRE(step >= 1 && Cp >= C && ld >= Cp, "mk_ncdhw_to_nhwc: bad args");
+    int Hd = H / step, Wd = W / step;
+    long long total = (long long)B * D * Hd * Wd * Cp;
+    if (total == 0) return 0;
+    k_ncdhw_to_nhwc<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, C, D, Hd, Wd, sb, sc, sd,
+                                                                                      sh, sw, step, dst, Cp, ld, total);
+    return mk_check_launch("mk_ncdhw_to_nhwc");
+}
+
+__global__ void k_nhwc_to_ncdhw(const float* __restrict__ src, int ld, int C, int D, int Hs, int Ws, int step,
+                                float* __restrict__ dst, long long sb, long long sc, long long sd, long long sh,
+                                long long sw, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    // iterate in destination order (w fastest) so the NCDHW writes coalesce when sw == 1
+    int w = (int)(i % Ws);
+    long long t = i / Ws;
+    int h = (int)(t % Hs);
+    t /= Hs;
+    int d = (int)(t % D);
+    t /= D;
+    int c = (int)(t % C);
+    long long b = t / C;
+    long long n = b * D + d;
+    float v = src[((n * Hs + h) * Ws + w) * ld + c];
+    dst[b * sb + c * sc + d * sd + (long long)h * step * sh + (long long)w * step * sw] = v;
+}
+
+MK_EXPORT int mk_nhwc_to_ncdhw(const float* src, int ld, int B, int C, int D, int Hs, int Ws, int step, float* dst,
+                               long long sb, long long sc, long long sd, long long sh, long long sw, void* stream) {
+    long long total = (long long)B * C * D * Hs * Ws;
+    if (total == 0) return 0;
+    k_nhwc_to_ncdhw<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, C, D, Hs, Ws, step, dst,
+                                                                                      sb, sc, sd, sh, sw, total);
+    return mk_check_launch("mk_nhwc_to_ncdhw");
+}
+
+// ------------------------------------------------------------------------------------------------ channel slices
+template <bool ADD>
+__global__ void k_copy_channels(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
+                                long long npix, int cv) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = npix * cv;
+    for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long p = i / cv;
+        int c = (int)(i % cv) * 4;
+        float4 v = ld4(src + p * lds + c);
+        if (ADD) v = v + ld4(dst + p * ldd + c);
+        st4(dst + p * ldd + c, v);
+    }
+}
+
+static int copy_channels_impl(bool add, const float* src, int lds, float* dst, int ldd, long long npix, int C,
+                              void* stream) {
+    MK_REQUIRE(C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "copy_channels: C/ld must be multiples of 4");
+    long long total = npix * (C / 4);
+    if (total == 0) return 0;
+    long long blocks = mk_cdiv(total, 256);
+    long long cap = (long long)mk_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (add)
+        k_copy_channels<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, npix, C / 4);
+    else
+        k_copy_channels<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, npix, C / 4);
+    return mk_check_launch("copy_channels");
+}
+
+MK_EXPORT int mk_copy_channels(const float* src, int lds, float* dst, int ldd, long long npix, int C, void* stream) {
+    return copy_channels_impl(false, src, lds, dst, ldd, npix, C, stream);
+}
+MK_EXPORT int mk_add_channels(const float* src, int lds, float* dst, int ldd, long long npix, int C, void* stream) {
+    return copy_channels_impl(true, src, lds, dst, ldd, npix, C, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ fused Adam
+// train.py:81-83: Adam(lr, betas=(0.5,0.999)), eps 1e-8, no weight decay.  One flat span; float4 main + tail.
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
+                       float bc2) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float step = lr / bc1;
+    const float rs = 1.f / sqrtf(bc2);
+    for (; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i];
+        float mi = b1 * m[i] + (1.f - b1) * gi;
+        float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float denom = sqrtf(vi) * rs + eps;
+        p[i] = p[i] - step * (mi / denom);
+    }
+}
+
+MK_EXPORT int mk_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                           float beta2, float eps, float bias_c1, float bias_c2, void* stream) {
+    if (n <= 0) return 0;
+    long long blocks = mk_cdiv(n, 256);
+    long long cap = (long long)mk_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    k_adam<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_c1, bias_c2);
+    return mk_check_launch("mk_adam_step");
+}
+
+// ------------------------------------------------------------------------------------------------ sigmoid backward
+__global__ void k_sigmoid_bwd(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dz,
+                              long long nv) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = ld4(y + i * 4), g = ld4(dy + i * 4);
+        st4(dz + i * 4, make_float4(g.x * a.x * (1.f - a.x), g.y * a.y * (1.f - a.y), g.z * a.z * (1.f - a.z),
+                                    g.w * a.w * (1.f - a.w)));
+    }
+}
+
+MK_EXPORT int mk_sigmoid_bwd(const float* y, const float* dy, float* dz, long long n, void* stream) {
+    MK_REQUIRE(n % 4 == 0, "mk_sigmoid_bwd: n must be x4");
+    if (n == 0) return 0;
+    long long blocks = mk_cdiv(n / 4, 256);
+    long long cap = 16LL * mk_num_sms();
+    if (blocks > cap) blocks = cap;
+    k_sigmoid_bwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, dy, dz, n / 4);
+    return mk_check_launch("mk_sigmoid_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------ channel gather
+// dst[p][j] = map[j] >= 0 ? src[p][map[j]] : 0.  Compacts a concat-with-holes tensor into a dense padded one (and,
+// with the inverse map, scatters gradients back).  Used once per generator pass (decoder output -> ResBlocks).
+__global__ void k_gather_channels(const float* __restrict__ src, int lds, const int* __restrict__ map,
+                                  float* __restrict__ dst, int ldd, long long npix, int Cd) {
+    long long total = npix * Cd;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long p = i / Cd;
+        int j = (int)(i % Cd);
+        int s = map[j];
+        dst[p * ldd + j] = s >= 0 ? src[p * lds + s] : 0.f;
+    }
+}
+
+MK_EXPORT int mk_gather_channels(const float* src, int lds, const int* map, float* dst, int ldd, long long npix,
+                                 int Cd, void* stream) {
+    long long total = npix * Cd;
+    if (total == 0) return 0;
+    long long blocks = mk_cdiv(total, 256);
+    long long cap = 16LL * mk_num_sms();
+    if (blocks > cap) blocks = cap;
+    k_gather_channels<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, map, dst, ldd, npix, Cd);
+    return mk_check_launch("mk_gather_channels");
+}

@@ -1,0 +1,99 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch; gloo in CPU tests).
+
+Replaces the reference's single-process DataParallel + thread-rendezvous sync-BN (sync_batchnorm/batchnorm.py:90-125,
+sync_batchnorm/comm.py) with
+  * ONE all-reduce of the packed `[sum x | sum x^2]` (2*Cp floats) per BN layer in forward and ONE of
+    `[sum dz | sum dz*xhat]` in backward, issued on the compute stream;
+  * one bucketed gradient all-reduce (average) per optimiser step (`GradSync`).
+The batch is sharded on dim 0 with equal shares per rank (train.py:99 uses drop_last=True), so the global pixel
+count is world_size x the local one.  The data path itself needs no other collective.
+"""
+import torch
+import torch.distributed as dist
+
+_sync_bn = True
+
+
+def set_sync_bn(enabled):
+    global _sync_bn
+    _sync_bn = bool(enabled)
+
+
+def world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def stats_world():
+    return world() if _sync_bn else 1
+
+
+def all_reduce_stats(t):
+    """Sum-all-reduce a packed statistics tensor in place; returns the factor the local count must be scaled by."""
+    w = stats_world()
+    if w > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return w
+
+
+def combine_stats(sum_x, sum_x2, count, eps=1e-5):
+    """Host-side restatement of mk_norm_finalize for tests: mean, invstd (biased) and unbiased variance."""
+    mean = sum_x / count
+    var = (sum_x2 / count - mean * mean).clamp_min(0)
+    return mean, (var + eps).rsqrt(), var * count / max(count - 1, 1)
+
+
+class GradSync:
+    """Bucketed gradient averaging across ranks (the DDP-style replacement of DataParallel's reduce-to-GPU-0).
+
+    Parameters are flattened into buckets of ~`bucket_mb`; `sync()` all-reduces every bucket that has gradients and
+    scatters the averages back.  Call it once between backward() and optimizer.step()."""
+
+    def __init__(self, params, bucket_mb=64):
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets, cur, size = [], [], 0
+        limit = bucket_mb * (1 << 20) // 4
+        for p in self.params:
+            cur.append(p)
+            size += p.numel()
+            if size >= limit:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+
+    def sync(self):
+        w = world()
+        if w == 1:
+            return
+        for bucket in self.buckets:
+            grads = [p.grad for p in bucket if p.grad is not None]
+            if not grads:
+                continue
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.div_(w)
+            off = 0
+            for g in grads:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n
+
+
+def shard_batch(x, dim=0):
+    """This rank's contiguous share of a global batch (DataParallel scatter semantics, train.py:104-110)."""
+    w, r = world(), rank()
+    if w == 1:
+        return x
+    if isinstance(x, dict):
+        return {k: shard_batch(v, dim) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return type(x)(shard_batch(v, dim) for v in x)
+    if torch.is_tensor(x):
+        n = x.shape[dim]
+        assert n % w == 0, 'global batch %d must divide by world size %d' % (n, w)
+        return x.narrow(dim, r * (n // w), n // w)
+    return x

@@ -1,0 +1,169 @@
+"""Shared test helpers: synthetic inputs, config loading, comparison metrics."""
+import os
+
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_config(name):
+    with open(os.path.join(ROOT, 'config', name + '.yaml')) as f:
+        return yaml.safe_load(f)
+
+
+def tiny_config():
+    """A small architecture exercising every code path (group blocks, clip_variance, use_difference)."""
+    cfg = load_config('taichi')
+    mp = cfg['model_params']
+    mp['common_params']['num_kp'] = 3
+    mp['kp_detector_params'].update(block_expansion=4, max_features=16, num_blocks=2)
+    g = mp['generator_params']
+    g.update(block_expansion=4, max_features=16, num_blocks=2, num_refinement_blocks=1)
+    g['dense_motion_params'].update(block_expansion=4, max_features=16, num_blocks=2)
+    mp['discriminator_params'].update(block_expansion=4, max_features=16, num_blocks=2)
+    cfg['train_params']['loss_weights']['reconstruction'] = [10, 10, 1]
+    return cfg
+
+
+def smooth_frames(b, d, res, seed):
+    """Well-conditioned synthetic frames (sums of gaussian blobs), (B,3,D,res,res) in [0,1].  Uniform noise makes
+    the warp / soft-argmax chain chaotic at fp32 (1e-7 input differences -> 1e-3 outputs), smooth frames do not."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, res), torch.linspace(-1, 1, res), indexing='ij')
+    out = torch.zeros(b, 3, d, res, res)
+    for i in range(b):
+        for j in range(d):
+            for c in range(3):
+                acc = torch.full_like(xx, 0.5)
+                for _ in range(4):
+                    r = torch.rand(4, generator=g)
+                    cx, cy = r[0].item() * 1.6 - 0.8, r[1].item() * 1.6 - 0.8
+                    s, a = 0.15 + 0.5 * r[2].item(), 0.8 * r[3].item() - 0.4
+                    acc = acc + a * torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+                out[i, c, j] = acc.clamp(0, 1)
+    return out
+
+
+def perturb_flow_head(generator, seed=1, std=0.05):
+    """The dense-motion head is zero-initialised (identity flow); give it seeded weights so warps are non-trivial."""
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(seed)
+        w = generator.dense_motion_module.hourglass.decoder.conv.weight
+        w.copy_(torch.randn(w.shape, generator=g) * std)
+
+
+def max_abs(a, b):
+    return (a.detach().cpu().float() - b.detach().cpu().float()).abs().max().item()
+
+
+def rel_err(a, b):
+    a, b = a.detach().cpu().float(), b.detach().cpu().float()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+
+
+def structurally_zero_grad(name):
+    """Parameters whose true gradient is exactly zero (pure rounding noise in both implementations): conv biases
+    that feed a batch/instance norm, and the bias in front of the spatial softmax."""
+    if not name.endswith('conv.bias') and not name.endswith('conv1.bias') and not name.endswith('conv2.bias'):
+        return False
+    if name.endswith('conv2.bias') or name == 'conv.bias' or 'conv-last' in name:
+        return False
+    if name.endswith('decoder.conv.bias'):
+        return name.startswith('predictor')  # KP head: softmax is shift invariant
+    if name.startswith('down_blocks.0.conv'):
+        return False  # discriminator block 0 has no norm
+    return True
+
+
+# ----------------------------------------------------------------------------------------------------- golden protocol
+def state_checksum(sd):
+    tot = 0.0
+    for i, (k, v) in enumerate(sorted(sd.items())):
+        tot += float(v.detach().cpu().double().abs().sum()) * (1 + (i % 7))
+    return tot
+
+
+def split(kj, detach=False):
+    f = (lambda t: t.detach()) if detach else (lambda t: t)
+    return ({k: f(v[:, 1:]) for k, v in kj.items()}, {k: f(v[:, :1]) for k, v in kj.items()})
+
+
+def run_protocol(gen, disc, kp, cfg, x, gen_loss_fn, disc_loss_fn):
+    """The exact sequence oracle/make_golden.py ran on the reference; works for the oracle (CPU) and the product
+    (CUDA) because both expose the reference's module API.  Returns a dict of CPU tensors / floats."""
+    import torch
+    tp = cfg['train_params']
+    out = {}
+    for m in (gen, disc, kp):
+        m.train()
+    kp_joined = kp(torch.cat([x['source'], x['video']], dim=2))
+    out['kp_mean'], out['kp_var'] = kp_joined['mean'], kp_joined['var']
+    kd, ks = split(kp_joined)
+    generated = gen(x['source'], kp_driving=kd, kp_source=ks)
+    out['video_prediction'], out['video_deformed'] = generated['video_prediction'], generated['video_deformed']
+    maps_gen = disc(generated['video_prediction'], kp_driving=kd, kp_source=ks)
+    maps_real = disc(x['video'], kp_driving=kd, kp_source=ks)
+    losses = gen_loss_fn(maps_gen, maps_real, generated['video_deformed'], tp['loss_weights'])
+    out['g_losses'] = torch.stack([l for l in losses])
+    out['disc_score_gen'] = maps_gen[-1]
+    sum(l.mean() for l in losses).backward()
+    gn = {}
+    for tag, m in (('G', gen), ('D', disc), ('K', kp)):
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                gn['gnorm/%s/%s' % (tag, k)] = float(p.grad.norm())
+    kdd, ksd = split(kp_joined, True)
+    d_loss = disc_loss_fn(disc(generated['video_prediction'].detach(), kp_driving=kdd, kp_source=ksd),
+                          disc(x['video'], kp_driving=kdd, kp_source=ksd), tp['loss_weights'])
+    out['d_losses'] = torch.stack([l for l in d_loss])
+    for m in (gen, disc, kp):
+        m.eval()
+    with torch.no_grad():
+        kpe = kp(torch.cat([x['source'], x['video']], dim=2))
+        kd, ks = split(kpe)
+        ge = gen(x['source'], kp_driving=kd, kp_source=ks)
+    out['eval_kp_mean'], out['eval_video_prediction'] = kpe['mean'], ge['video_prediction']
+    out = {k: v.detach().cpu() for k, v in out.items()}
+    out.update(gn)
+    return out
+
+
+GOLDEN_TOL = {'kp_mean': 2e-5, 'kp_var': 2e-5, 'video_prediction': 1e-3, 'video_deformed': 2e-3, 'g_losses': 2e-3,
+              'd_losses': 1e-3, 'disc_score_gen': 2e-3, 'eval_kp_mean': 2e-5, 'eval_video_prediction': 1e-3}
+
+
+def compare_with_golden(out, gold, grad_tol=2e-2, scale=1.0):
+    """max-abs on outputs (tolerances above; generator output <= 1e-3 is the north-star bar) and relative error on
+    per-parameter gradient norms, skipping parameters whose true gradient is zero (rounding noise)."""
+    import numpy as np
+    report = {}
+    for k, tol in GOLDEN_TOL.items():
+        err = float(np.abs(out[k].numpy() - gold[k]).max())
+        report[k] = err
+        assert err <= tol * scale, (k, err, tol * scale)
+    worst = 0.0
+    for k in gold.files:
+        if not k.startswith('gnorm/'):
+            continue
+        name = k.split('/', 2)[2]
+        g = float(gold[k])
+        if structurally_zero_grad(name) or g < 1e-6:
+            continue
+        assert k in out, k
+        err = abs(out[k] - g) / g
+        worst = max(worst, err)
+        assert err <= grad_tol * scale, (k, out[k], g)
+    report['worst_gradnorm_rel'] = worst
+    return report
+
+
+def load_golden(name):
+    import numpy as np
+    return np.load(os.path.join(ROOT, 'tests', 'golden', name + '.npz'))
+
+
+def golden_weights(gold, tag):
+    import torch
+    pre = 'w/%s/' % tag
+    return {k[len(pre):]: torch.from_numpy(gold[k].copy()) for k in gold.files if k.startswith(pre)}

@@ -1,0 +1,163 @@
+"""Module- and step-level parity of the drop-in `modules/*` (CUDA kernels) against the CPU oracle and against the
+golden fixtures recorded from the unmodified reference.  Bars: keypoints <= 2e-5, generator output <= 1e-3 max-abs
+(north-star), gradients compared through per-parameter norms / direct tensors at 2e-2 / 2e-3 relative."""
+import pytest
+import torch
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def build_product(cfg, seed=0, perturb=True):
+    from modules.generator import MotionTransferGenerator
+    from modules.discriminator import Discriminator
+    from modules.keypoint_detector import KPDetector
+    mp = cfg['model_params']
+    torch.manual_seed(seed)
+    gen = MotionTransferGenerator(**mp['generator_params'], **mp['common_params'])
+    disc = Discriminator(**mp['discriminator_params'], **mp['common_params'])
+    kp = KPDetector(**mp['kp_detector_params'], **mp['common_params'])
+    if perturb:
+        helpers.perturb_flow_head(gen)
+    return gen, disc, kp
+
+
+def product_losses():
+    from modules import losses
+    return losses.generator_loss, losses.discriminator_loss
+
+
+def test_golden_tiny():
+    gold = helpers.load_golden('golden_tiny')
+    cfg = helpers.tiny_config()
+    gen, disc, kp = build_product(cfg)
+    for tag, m in (('G', gen), ('D', disc), ('K', kp)):
+        m.load_state_dict(helpers.golden_weights(gold, tag))
+        m.cuda()
+    x = {'source': torch.from_numpy(gold['source']).cuda(), 'video': torch.from_numpy(gold['video']).cuda()}
+    gl, dl = product_losses()
+    rep = helpers.compare_with_golden(helpers.run_protocol(gen, disc, kp, cfg, x, gl, dl), gold)
+    print(rep)
+
+
+def test_golden_shapes():
+    gold = helpers.load_golden('golden_shapes')
+    cfg = helpers.load_config('shapes')
+    gen, disc, kp = build_product(cfg)
+    assert [helpers.state_checksum(m.state_dict()) for m in (gen, disc, kp)] == list(gold['checksum'])
+    for m in (gen, disc, kp):
+        m.cuda()
+    x = {'source': torch.from_numpy(gold['source']).cuda(), 'video': torch.from_numpy(gold['video']).cuda()}
+    gl, dl = product_losses()
+    rep = helpers.compare_with_golden(helpers.run_protocol(gen, disc, kp, cfg, x, gl, dl), gold)
+    print(rep)
+
+
+def _pair(cfg, res, batch, d=1):
+    """product nets on CUDA + oracle nets on CPU with identical weights, plus inputs."""
+    from oracle import monkey_oracle as mo
+    gen, disc, kp = build_product(cfg)
+    og, od, ok = mo.build_from_config(cfg)
+    og.load_state_dict(gen.state_dict()); od.load_state_dict(disc.state_dict()); ok.load_state_dict(kp.state_dict())
+    for m in (gen, disc, kp):
+        m.cuda()
+    x = {'source': helpers.smooth_frames(batch, 1, res, 5), 'video': helpers.smooth_frames(batch, d, res, 6)}
+    return (gen, disc, kp), (og, od, ok), x
+
+
+@pytest.mark.parametrize('name,res', [('moving-gif', 64), ('vox-full', 128), ('bair', 64), ('taichi', 64)])
+def test_forward_parity_configs(name, res):
+    """eval-mode forward of every architecture variant: scale_factor 0.5/0.25, use_difference, trilinear,
+    'sum' normalisation, 6/7-block generators.  Identical keypoints are fed to both generators."""
+    cfg = helpers.load_config(name)
+    (gen, disc, kp), (og, od, ok), x = _pair(cfg, res, 1, d=2)
+    for m in (gen, disc, kp, og, od, ok):
+        m.eval()
+    with torch.no_grad():
+        a = kp(x['video'].cuda())
+        b = ok(x['video'])
+        assert helpers.max_abs(a['mean'], b['mean']) < 2e-5 and helpers.max_abs(a['var'], b['var']) < 2e-5
+        res_px = x['video'].shape[-1]
+        assert torch.equal(torch.round(res_px * (a['mean'].cpu() + 1) / 2), torch.round(res_px * (b['mean'] + 1) / 2))
+        ks = {k: v[:, :1] for k, v in b.items()}
+        oa = og(x['source'], kp_driving=b, kp_source=ks)
+        bc = {k: v.cuda() for k, v in b.items()}
+        ksc = {k: v.cuda() for k, v in ks.items()}
+        ga = gen(x['source'].cuda(), kp_driving=bc, kp_source=ksc)
+        assert ga['video_prediction'].shape == oa['video_prediction'].shape
+        assert helpers.max_abs(ga['video_prediction'], oa['video_prediction']) < 1e-3
+        assert helpers.max_abs(ga['video_deformed'], oa['video_deformed']) < 1e-4
+        kd1 = {k: v[:, :1] for k, v in b.items()}
+        om = od(x['video'][:, :, :1], kd1, ks)
+        gm = disc(x['video'][:, :, :1].cuda(), {k: v.cuda() for k, v in kd1.items()}, ksc)
+        for p, q in zip(gm, om):
+            assert p.shape == q.shape
+            assert helpers.max_abs(p, q) < 1e-3 * max(1.0, float(q.abs().max()))
+
+
+def test_train_step_gradient_parity_tiny():
+    """Full G-step + D-step graphs: every parameter gradient against the oracle's autograd."""
+    from oracle import monkey_oracle as mo
+    cfg = helpers.tiny_config()
+    (gen, disc, kp), (og, od, ok), x = _pair(cfg, 32, 3)
+    tp = cfg['train_params']
+    for m in (gen, disc, kp, og, od, ok):
+        m.train()
+    out = mo.generator_full(ok, og, od, tp, x)
+    sum(v.mean() for v in out[:-2]).backward()
+    import train_glue
+    xg = {k: v.cuda() for k, v in x.items()}
+    pout = train_glue.generator_full(kp, gen, disc, tp, xg)
+    sum(v.mean() for v in pout[:-2]).backward()
+    for a, b in zip(pout[:-2], out[:-2]):
+        assert helpers.max_abs(a, b) < 2e-3
+    worst = 0.0
+    for (n1, p1), (n2, p2) in zip(list(gen.named_parameters()) + list(kp.named_parameters()) + list(disc.named_parameters()),
+                                  list(og.named_parameters()) + list(ok.named_parameters()) + list(od.named_parameters())):
+        assert n1 == n2
+        if p2.grad is None:
+            continue
+        if helpers.structurally_zero_grad(n1):
+            continue
+        assert p1.grad is not None, n1
+        e = helpers.rel_err(p1.grad, p2.grad)
+        worst = max(worst, e)
+        assert e < 5e-3, (n1, e)
+    print('worst relative gradient error', worst)
+    # discriminator step
+    for m in (gen, disc, kp, og, od, ok):
+        m.zero_grad()
+    dl = mo.discriminator_full(ok, og, od, tp, x, out[-1], out[-2])
+    sum(v.mean() for v in dl).backward()
+    pdl = train_glue.discriminator_full(kp, gen, disc, tp, xg, pout[-1], pout[-2])
+    sum(v.mean() for v in pdl).backward()
+    assert helpers.max_abs(pdl[0], dl[0]) < 2e-3
+    for (n1, p1), (n2, p2) in zip(disc.named_parameters(), od.named_parameters()):
+        if helpers.structurally_zero_grad(n1):
+            continue
+        assert helpers.rel_err(p1.grad, p2.grad) < 5e-3, n1
+
+
+def test_transfer_one_matches_oracle():
+    """transfer.py:65-79 composition in eval mode on the shapes architecture, d = 3 driving frames."""
+    from oracle import monkey_oracle as mo
+    cfg = helpers.load_config('shapes')
+    (gen, disc, kp), (og, od, ok), x = _pair(cfg, 64, 1, d=3)
+    for m in (gen, kp, og, ok):
+        m.eval()
+    norm = cfg['transfer_params']['normalization_params']
+    norm = {k: v for k, v in norm.items()}
+    with torch.no_grad():
+        ref = mo.transfer_one(og, ok, x['source'], x['video'], norm)
+        out = mo.transfer_one(gen, kp, x['source'].cuda(), x['video'].cuda(), norm)  # same driver, product modules
+    assert helpers.max_abs(out['kp_driving']['mean'], ref['kp_driving']['mean']) < 2e-5
+    assert helpers.max_abs(out['video_prediction'], ref['video_prediction']) < 1e-3
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    cfg = helpers.tiny_config()
+    gen, disc, kp = build_product(cfg)
+    kp.cuda()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        kp(torch.rand(1, 3, 1, 32, 32))
