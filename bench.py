@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py - frames/sec of the Monkey-Net training step (BASELINE.json configs[1]: config/shapes.yaml nets, batch 32
+synthetic 64x64 frame pairs per GPU, full train.py:110-136 iteration body: G fwd+bwd + Adam(G,KP) + D fwd+bwd +
+Adam(D)) on N x B200, one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU restatement of the reference (oracle) on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs resident in HBM; `e2e` = same metric through
+the public API (DataParallelWithCallback(GeneratorFullModel)(x)) with pinned HOST inputs, H2D copy and D2H loss read
+inside the timed region; `roofline` = conv kernels' algorithmic FLOP/s vs the measured tensor peak;
+`cpu_baseline` = the oracle port timed on this box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import torch  # noqa: E402
+import yaml  # noqa: E402
+
+METRIC = 'frames/sec (training step: G fwd+bwd+Adam, D fwd+bwd+Adam)'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='shapes')
+    ap.add_argument('--res', type=int, default=64)
+    ap.add_argument('--batch', type=int, default=32, help='frame pairs PER GPU (weak scaling)')
+    ap.add_argument('--cpu-batch', type=int, default=None, help='batch of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-kernel-bench', action='store_true')
+    return ap.parse_args()
+
+
+def load_config(name):
+    with open(os.path.join(ROOT, 'config', name + '.yaml')) as f:
+        return yaml.safe_load(f)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'],
+                'bf16_tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+# ------------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def build_nets(cfg, device):
+    from modules.generator import MotionTransferGenerator
+    from modules.discriminator import Discriminator
+    from modules.keypoint_detector import KPDetector
+    mp = cfg['model_params']
+    torch.manual_seed(0)
+    gen = MotionTransferGenerator(**mp['generator_params'], **mp['common_params'])
+    disc = Discriminator(**mp['discriminator_params'], **mp['common_params'])
+    kp = KPDetector(**mp['kp_detector_params'], **mp['common_params'])
+    with torch.no_grad():  # non-trivial flow field
+        g = torch.Generator().manual_seed(1)
+        w = gen.dense_motion_module.hourglass.decoder.conv.weight
+        w.copy_(torch.randn(w.shape, generator=g) * 0.05)
+    return gen.to(device), disc.to(device), kp.to(device)
+
+
+def conv_flops_per_step(cfg, res, batch):
+    """Algorithmic conv FLOPs of one training iteration for `batch` samples: 3*KP2 + 3*G + 12*D, from
+    hooking every conv of the oracle (2*MACs, forward)."""
+    from oracle import monkey_oracle as mo
+    og, od, ok = mo.build_from_config(cfg)
+    for m in (og, od, ok):
+        for p in m.parameters():
+            torch.nn.init.normal_(p, std=0.01)
+        m.eval()
+    x = torch.rand(1, 3, 1, res, res)
+    with torch.no_grad():
+        kpj = ok(torch.cat([x, x], 2))
+    kd = {k: v[:, 1:] for k, v in kpj.items()}
+    ks = {k: v[:, :1] for k, v in kpj.items()}
+    f_kp = mo.conv_flops(ok, torch.cat([x, x], 2))
+    f_g = mo.conv_flops(og, x, kd, ks)
+    f_d = mo.conv_flops(od, x, kd, ks)
+    return {'kp2': f_kp, 'g': f_g, 'd': f_d, 'train_step_per_sample': 3 * f_kp + 3 * f_g + 12 * f_d,
+            'train_step': batch * (3 * f_kp + 3 * f_g + 12 * f_d)}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from monkey_net_b200 import lib, train_step
+    from sync_batchnorm import DataParallelWithCallback
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py (impl=ours) needs a CUDA device; there is no CPU fallback')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    lib.load()
+    cfg = load_config(args.config)
+    tp = cfg['train_params']
+    gen, disc, kp = build_nets(cfg, device)
+    opts = train_step.make_optimizers(gen, disc, kp, tp['lr'])
+    g_full = DataParallelWithCallback(train_step.GeneratorFullModel(kp, gen, disc, tp), device_ids=[local])
+    d_full = DataParallelWithCallback(train_step.DiscriminatorFullModel(kp, gen, disc, tp), device_ids=[local])
+    for m in (gen, disc, kp):
+        m.train()
+    B = args.batch
+    torch.manual_seed(100 + rank)
+    host = {'source': torch.rand(B, 3, 1, args.res, args.res).pin_memory(),
+            'video': torch.rand(B, 3, 1, args.res, args.res).pin_memory()}
+    resident = {k: v.to(device) for k, v in host.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s, e in evs:
+            lib.call('mk_fill_zero', flush.data_ptr(), flush.numel(), torch.cuda.current_stream().cuda_stream)
+            s.record()
+            step_fn()
+            e.record()
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_resident():
+        train_step.train_iteration(g_full, d_full, opts, tp, resident)
+
+    last = {}
+
+    def step_e2e():
+        g_vals, d_vals = train_step.train_iteration(g_full, d_full, opts, tp, host)  # facade does the H2D copy
+        last['loss'] = torch.stack([v.detach() for v in g_vals + d_vals]).cpu()       # D2H read of the step's result
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = lib.launches()
+    ms = timed(step_resident, args.steps)
+    launches = lib.launches() - n0 - args.steps  # minus the L2-flush memsets
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- roofline of the dominant kernel family (implicit-GEMM convolutions): device time by CUDA events around
+    # every conv launch on the launching stream, algorithmic FLOPs from the oracle's conv hooks
+    conv_ms = None
+    if rank == 0:
+        names = ('mk_conv2d', 'mk_conv2d_wgrad')
+        spans = []
+        orig = lib.call
+
+        def traced(name, *a):
+            if name in names:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(); orig(name, *a); e.record()
+                spans.append((s, e))
+            else:
+                orig(name, *a)
+        lib.call = traced
+        from monkey_net_b200 import ops as _ops
+        _ops.lib.call = traced
+        torch.cuda.synchronize()
+        t0 = time.time()
+        step_resident()
+        torch.cuda.synchronize()
+        lib.call = orig
+        _ops.lib.call = orig
+        conv_ms = sum(s.elapsed_time(e) for s, e in spans)
+        n_conv = len(spans)
+    if world > 1:
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    flops = conv_flops_per_step(cfg, args.res, B)
+    frames = B * world * args.steps
+    out = {
+        'metric': METRIC, 'value': frames / (ms / 1e3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (torch.rand frames, seeded default-init weights)',
+        'config': {'workload': 'config/%s.yaml training step, %d synthetic %dx%d frame pairs per GPU, 1 driving '
+                               'frame, fwd+bwd+Adam for G, KP and D' % (args.config, B, args.res, args.res),
+                   'global_batch': B * world, 'parallelism': 'dp%d' % world,
+                   'l2': 'flushed between timed steps (256 MiB memset, outside the per-step event pairs)',
+                   'conv_gflop_per_sample': flops['train_step_per_sample'] / 1e9},
+        'e2e': {'value': frames / (ms_e2e / 1e3), 'unit': 'frames/s',
+                'h2d_bytes_per_step': sum(v.numel() * 4 for v in host.values()),
+                'd2h_bytes_per_step': int(last['loss'].numel() * 4)},
+        'gpu_launches': launches,
+        'clocks': clocks,
+    }
+    achieved = flops['train_step'] / (conv_ms / 1e3) / 1e12
+    out['roofline'] = {'bound': 'tensor', 'kernel': 'k_conv_ffma/k_conv_wgrad (implicit-GEMM conv fwd, dgrad, wgrad)',
+                       'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                       'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
+                       'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
+                       'launches_per_step': n_conv, 'conv_ms_per_step': conv_ms,
+                       'conv_share_of_step': conv_ms / (ms / args.steps),
+                       'note': 'fp32 FFMA exact-parity path; algorithmic FLOPs = 3*KP2 + 3*G + 12*D conv FLOPs'}
+    if not args.no_kernel_bench:
+        out['kernels'] = kernel_bench(device, pk)
+    if not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_baseline(args, cfg)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_bench(device, pk):
+    """grid_sample HBM roofline on the large vox-full pyramid levels: algorithmic bytes
+    4*(B*C*h*w + 2*B*d*h*w + B*d*C*h*w) / CUDA-event time, L2 flushed between launches."""
+    from monkey_net_b200 import lib
+    st = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    res = {}
+    B, d = 16, 1
+    for (C, h) in ((64, 128), (128, 64), (4, 256)):
+        inp = torch.rand(B, h, h, C, device=device)
+        ys, xs = torch.meshgrid(torch.linspace(-1, 1, 256, device=device), torch.linspace(-1, 1, 256, device=device),
+                                indexing='ij')
+        deform = (torch.stack([xs, ys], -1)[None] + 0.05 * torch.randn(B * d, 256, 256, 2, device=device)).contiguous()
+        out = torch.empty(B * d, h, h, C, device=device)
+        times = []
+        for it in range(8):
+            lib.call('mk_fill_zero', flush.data_ptr(), flush.numel(), st)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            lib.call('mk_grid_sample_fwd', inp.data_ptr(), B, h, h, C, C, deform.data_ptr(), d, 256, 256, 0,
+                     out.data_ptr(), C, st)
+            e.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                times.append(s.elapsed_time(e))
+        ms = sum(times) / len(times)
+        logical_c = 3 if C == 4 else C
+        byts = 4 * (B * logical_c * h * h + 2 * B * d * h * h + B * d * logical_c * h * h)
+        gbs = byts / (ms / 1e3) / 1e9
+        res['grid_sample_fwd_%dx%d2' % (logical_c, h)] = {'ms': ms, 'achieved_gbs': gbs, 'frac_hbm': gbs / pk['hbm_gbs']}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------- CPU arms
+def oracle_step_time(cfg, res, batch, steps, warmup):
+    from oracle import monkey_oracle as mo
+    from modules.generator import MotionTransferGenerator
+    from modules.discriminator import Discriminator
+    from modules.keypoint_detector import KPDetector
+    mp, tp = cfg['model_params'], cfg['train_params']
+    torch.manual_seed(0)
+    pg = MotionTransferGenerator(**mp['generator_params'], **mp['common_params'])
+    pd = Discriminator(**mp['discriminator_params'], **mp['common_params'])
+    pk = KPDetector(**mp['kp_detector_params'], **mp['common_params'])
+    og, od, ok = mo.build_from_config(cfg)
+    og.load_state_dict(pg.state_dict()); od.load_state_dict(pd.state_dict()); ok.load_state_dict(pk.state_dict())
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(1)
+        w = og.dense_motion_module.hourglass.decoder.conv.weight
+        w.copy_(torch.randn(w.shape, generator=g) * 0.05)
+    for m in (og, od, ok):
+        m.train()
+    opts = mo.make_optimizers(og, od, ok, tp['lr'])
+    torch.manual_seed(100)
+    x = {'source': torch.rand(batch, 3, 1, res, res), 'video': torch.rand(batch, 3, 1, res, res)}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        mo.train_iteration(ok, og, od, opts, tp, x)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    return times[len(times) // 2]
+
+
+def cpu_baseline(args, cfg):
+    torch.set_num_threads(os.cpu_count())
+    b = args.cpu_batch or (args.batch if args.res <= 64 else 2)
+    t = oracle_step_time(cfg, args.res, b, steps=5, warmup=2)
+    return {'value': b / t, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': 'oracle/monkey_oracle.py (plain-PyTorch CPU restatement of the reference step), %s.yaml, '
+                      'batch %d @%dx%d, median of 5 steps after 2 warm-up' % (args.config, b, args.res, args.res)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path = the pinned oracle port (the reference itself
+    cannot travel to the GPU box and has no installable package), all host threads, bounded sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    cfg = load_config(args.config)
+    b = args.cpu_batch or (args.batch if args.res <= 64 else 2)
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    t = oracle_step_time(cfg, args.res, b, steps=steps, warmup=warm)
+    val = b / t
+    cb = {'value': val, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+          'sample': 'oracle port, %s.yaml, batch %d @%dx%d, median of %d steps' % (args.config, b, args.res, args.res,
+                                                                                   steps)}
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warm, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'config/%s.yaml training step, CPU, batch %d @%dx%d' % (args.config, b, args.res,
+                                                                                        args.res)},
+        'cpu_baseline': cb,
+        'e2e': {'value': val, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

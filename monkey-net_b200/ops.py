@@ -648,21 +648,21 @@ class _Loss(torch.autograd.Function):
         B, C, D, H, W = a.shape
         g = g.contiguous()
 
-        def grad_like(t):
-            # same strides as the operand; NHWC-backed views carry zero padding channels
-            if _is_nhwc_backed(t) and pad4(C) != C:
-                buf = _zeros(B * D, H, W, pad4(C), like=t)
-                return _nhwc_as_ncdhw(buf, B, C)
-            return torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device) \
-                if t.is_non_overlapping_and_dense() else torch.empty_like(t, memory_format=torch.contiguous_format)
+        def prep(t):
+            """(operand with kernel-friendly strides, gradient buffer sharing exactly those strides)"""
+            if _is_nhwc_backed(t):  # discriminator maps / generated frames: keep the channels-last memory
+                cp = pad4(C)
+                buf = _zeros(B * D, H, W, cp, like=t) if cp != C else _empty(B * D, H, W, cp, like=t)
+                return t, _nhwc_as_ncdhw(buf, B, C)
+            if not t.is_contiguous():
+                t = t.contiguous()
+            return t, torch.empty_like(t)
 
-        da = grad_like(a) if ctx.needs_input_grad[2] else None
-        db = grad_like(b) if (b is not None and ctx.needs_input_grad[3]) else None
-        # kernels index gradients with the operand strides, so the grad buffers must share them
-        if da is not None and da.stride() != a.stride():
-            a = a.contiguous()
-        if db is not None and db.stride() != b.stride():
-            b = b.contiguous()
+        da = db = None
+        if ctx.needs_input_grad[2]:
+            a, da = prep(a)
+        if b is not None and ctx.needs_input_grad[3]:
+            b, db = prep(b)
         sa = _strides5(a)
         sb = _strides5(b) if b is not None else None
         lib.call('mk_loss_bwd', kind, a.data_ptr(), sa, _ptr(b), sb, B, C, D, H, W, weight, g.data_ptr(), _ptr(da),

@@ -84,6 +84,12 @@ def state_checksum(sd):
     return tot
 
 
+def assert_checksums(got, want):
+    """state_dict checksums are double-precision sums: equal up to summation order across CPUs."""
+    for a, b in zip(got, want):
+        assert abs(a - float(b)) <= 1e-10 * abs(float(b)), ('default init differs from the reference', a, float(b))
+
+
 def split(kj, detach=False):
     f = (lambda t: t.detach()) if detach else (lambda t: t)
     return ({k: f(v[:, 1:]) for k, v in kj.items()}, {k: f(v[:, :1]) for k, v in kj.items()})

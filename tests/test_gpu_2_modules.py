@@ -45,7 +45,7 @@ def test_golden_shapes():
     gold = helpers.load_golden('golden_shapes')
     cfg = helpers.load_config('shapes')
     gen, disc, kp = build_product(cfg)
-    assert [helpers.state_checksum(m.state_dict()) for m in (gen, disc, kp)] == list(gold['checksum'])
+    helpers.assert_checksums([helpers.state_checksum(m.state_dict()) for m in (gen, disc, kp)], gold['checksum'])
     for m in (gen, disc, kp):
         m.cuda()
     x = {'source': torch.from_numpy(gold['source']).cuda(), 'video': torch.from_numpy(gold['video']).cuda()}

@@ -25,7 +25,7 @@ def _oracle_protocol(cfg, gold, weights_from_gold):
         pk = KPDetector(**mp['kp_detector_params'], **mp['common_params'])
         helpers.perturb_flow_head(pg)
         sums = [helpers.state_checksum(m.state_dict()) for m in (pg, pd, pk)]
-        assert sums == list(gold['checksum']), 'default init differs from the reference'
+        helpers.assert_checksums(sums, gold['checksum'])
         gen.load_state_dict(pg.state_dict()); disc.load_state_dict(pd.state_dict()); kp.load_state_dict(pk.state_dict())
     x = {'source': torch.from_numpy(gold['source']), 'video': torch.from_numpy(gold['video'])}
     return helpers.run_protocol(gen, disc, kp, cfg, x, mo.generator_loss, mo.discriminator_loss)
