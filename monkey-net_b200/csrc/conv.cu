@@ -396,11 +396,22 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (bias_p && i < Cout_p) bias_p[i] = (bias && i < Co) ? bias[i] : 0.f;
     if (i >= total) return;
+    // modes 2/3 = modes 0/1 in the tensor-core layout [tap][Kout][Kin] (K-major rows), values rounded to TF32
+    const int tc = mode >> 1;
+    mode &= 1;
     const int Kin = mode == 0 ? Cin_p : Cout_p, Kout = mode == 0 ? Cout_p : Cin_p;
-    int ko = (int)(i % Kout);
-    long long t = i / Kout;
-    int ki = (int)(t % Kin);
-    int tap = (int)(t / Kin);
+    int ko, ki, tap;
+    if (tc) {
+        ki = (int)(i % Kin);
+        long long t = i / Kin;
+        ko = (int)(t % Kout);
+        tap = (int)(t / Kout);
+    } else {
+        ko = (int)(i % Kout);
+        long long t = i / Kout;
+        ki = (int)(t % Kin);
+        tap = (int)(t / Kin);
+    }
     int r = tap / S, s = tap - r * S;
     int ci_p = mode == 0 ? ki : ko, co = mode == 0 ? ko : ki;
     if (mode == 1) { r = R - 1 - r; s = S - 1 - s; }
@@ -411,6 +422,11 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
         int g = co / cog;
         int cil = ci - g * Cig;
         if (cil >= 0 && cil < Cig) v = w[(((long long)co * Cig + cil) * R + r) * S + s];
+    }
+    if (tc) {
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        v = __uint_as_float(u);
     }
     wp[i] = v;
 }

@@ -1,0 +1,321 @@
+// Tensor-core convolution for sm_100a: TMA-tiled implicit GEMM on tcgen05 (kind::tf32) with TMEM accumulators.
+//
+//   D[128 pixels][BN couts] += A[128 pixels][32 ch] * B[BN couts][32 ch]^T      per (filter tap, 32-channel chunk)
+//
+// * A tile = ONE 4-D TMA box {32 ch, TW, TH, TN} of the NHWC activation, shifted by the tap offset; out-of-bounds
+//   pixels / channels are zero-filled by the TMA unit, which IS the convolution's zero padding (and the K padding
+//   of ragged channel counts).  The box lands in shared memory as 128 rows x 128 B with the 128B swizzle - exactly
+//   the canonical K-major UMMA operand layout, so no thread ever touches the operands.
+// * B tile = 3-D TMA box {32 ch, BN, 1} of the weights packed [tap][Cout_p][Cin_p] (K-major, pre-rounded to TF32).
+// * warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane, tcgen05.mma, commit -> frees the
+//   smem stage), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld 32x32b -> registers -> affine, residual,
+//   activation -> 128-bit stores).  smem ring of STAGES stages with full/empty mbarriers; accumulator handed over
+//   through a tmem_full mbarrier.  3 x 32 KB stages keep two CTAs resident per SM, so one CTA's epilogue overlaps
+//   the other's MMA stream.
+// Same contract as mk_conv2d (conv.cu) for stride-1 convs without the upsample / pool options.
+#include "common.cuh"
+#include "../../include/monkey_b200.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;        // output pixels per CTA (UMMA M)
+constexpr int BN_MAX = 128;    // output channels per CTA (UMMA N <= 128)
+constexpr int KC = 32;         // fp32 channels per stage = 128 bytes = one swizzle row
+constexpr int STAGES = 3;
+constexpr int A_BYTES = BM * KC * 4;
+constexpr int B_BYTES = BN_MAX * KC * 4;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcP {
+    int N, Ho, Wo, Cout_p, ldy, Cin_p, R, S, pad;
+    int TW, TH, TN, tilesW, tilesH;
+    const float* scale; const float* shift; const float* resid; int ldr, act; float slope;
+    float* y;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();  // a protocol bug must abort, never hang the GPU box
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// K-major, 128B-swizzled operand: rows of 128 B, 8-row atoms of 1024 B (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                  // D = F32
+    d |= 2u << 7;                  // A = TF32
+    d |= 2u << 10;                 // B = TF32
+    d |= (uint32_t)(n >> 3) << 17; // N
+    d |= (uint32_t)(m >> 4) << 24; // M
+    return d;                      // a_major = b_major = 0 (K-major), no negate, dense
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtensorMap tmA,
+                                                 const __grid_constant__ CUtensorMap tmB, const TcP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % p.tilesW; t /= p.tilesW;
+    const int th = t % p.tilesH; t /= p.tilesH;
+    const int w0 = tw * p.TW, h0 = th * p.TH, n0 = t * p.TN;
+    const int cout0 = blockIdx.y * BN_MAX;
+    const int n_this = min(BN_MAX, p.Cout_p - cout0);
+    const int nchunks = (p.Cin_p + KC - 1) / KC;
+    const int niter = p.R * p.S * nchunks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)BN_MAX)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (elect_one()) {
+            for (int it = 0; it < niter; ++it) {
+                const int stage = it % STAGES;
+                const uint32_t phase = (it / STAGES) & 1;
+                const int tap = it / nchunks, ch = it - tap * nchunks;
+                const int r = tap / p.S, s = tap - r * p.S;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* a = smem + stage * STAGE_BYTES;
+                mbar_expect_tx(&full[stage], STAGE_BYTES);
+                tma_load_4d(a, &tmA, &full[stage], ch * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
+                tma_load_3d(a + A_BYTES, &tmB, &full[stage], ch * KC, cout0, tap);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        const uint32_t idesc = umma_idesc_tf32(BM, n_this);
+        for (int it = 0; it < niter; ++it) {
+            const int stage = it % STAGES;
+            const uint32_t phase = (it / STAGES) & 1;
+            const int ch = it % nchunks;
+            mbar_wait(&full[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint8_t* a = smem + stage * STAGE_BYTES;
+                const uint64_t adesc = umma_desc(a), bdesc = umma_desc(a + A_BYTES);
+                int kleft = p.Cin_p - ch * KC;
+                if (kleft > KC) kleft = KC;
+                const int nk = (kleft + 7) >> 3;  // UMMA K = 8 tf32 (32 bytes); the TMA zero-fills the ragged tail
+                for (int k = 0; k < nk; ++k)      // advancing 32 B inside the 128 B swizzle row = +2 in 16 B units
+                    umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) ? 1u : 0u);
+                umma_commit(&empty[stage]);       // frees the smem stage when these MMAs retire
+                if (it == niter - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue
+        const int q = warp & 3;               // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;        // GEMM row = pixel of the tile, TMA box order (w fastest, then h, n)
+        const int iw = row % p.TW;
+        const int ih = (row / p.TW) % p.TH;
+        const int in_ = row / (p.TW * p.TH);
+        const int n = n0 + in_, h = h0 + ih, w = w0 + iw;
+        const bool valid = n < p.N && h < p.Ho && w < p.Wo;
+        const long long pix = ((long long)n * p.Ho + h) * p.Wo + w;
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < n_this; c += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (!valid) continue;
+            const int co = cout0 + c;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                float4 sc = p.scale ? ldg4(p.scale + co + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+                float4 sh = p.shift ? ldg4(p.shift + co + j) : f4zero();
+                float4 o = make_float4(fmaf(v[j], sc.x, sh.x), fmaf(v[j + 1], sc.y, sh.y), fmaf(v[j + 2], sc.z, sh.z),
+                                       fmaf(v[j + 3], sc.w, sh.w));
+                if (p.resid) o = o + ldg4(p.resid + pix * p.ldr + co + j);
+                if (p.act == 1) {
+                    o.x = o.x > 0.f ? o.x : o.x * p.slope; o.y = o.y > 0.f ? o.y : o.y * p.slope;
+                    o.z = o.z > 0.f ? o.z : o.z * p.slope; o.w = o.w > 0.f ? o.w : o.w * p.slope;
+                } else if (p.act == 2) {
+                    o.x = 1.f / (1.f + expf(-o.x)); o.y = 1.f / (1.f + expf(-o.y));
+                    o.z = 1.f / (1.f + expf(-o.z)); o.w = 1.f / (1.f + expf(-o.w));
+                }
+                st4(p.y + pix * p.ldy + co + j, o);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN_MAX)
+                     : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int pow2_ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+// Returns 0 on success, -2 if the shape is outside this kernel's envelope (caller uses mk_conv2d instead).
+MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc, int R,
+                           int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
+                           float slope, float* y, int Cout_p, int ldy, void* stream) {
+    if (Cin_p % 4 || ldx % 4 || Cout_p % 16 || ldy % 4 || Cin_p < 8 || (resid && ldr % 4)) {
+        mk_set_error("mk_conv2d_tc: unsupported channel configuration");
+        return -2;
+    }
+    EncodeTiledFn encode = get_encode();
+    MK_REQUIRE(encode != nullptr, "mk_conv2d_tc: cuTensorMapEncodeTiled unavailable");
+    TcP p;
+    p.N = N; p.Ho = Hin + 2 * pad - R + 1; p.Wo = Win + 2 * pad - S + 1;
+    MK_REQUIRE(p.Ho > 0 && p.Wo > 0, "mk_conv2d_tc: empty output");
+    p.Cout_p = Cout_p; p.ldy = ldy; p.Cin_p = Cin_p; p.R = R; p.S = S; p.pad = pad;
+    p.TW = pow2_ceil(p.Wo) < 16 ? pow2_ceil(p.Wo) : 16;
+    p.TH = pow2_ceil(p.Ho) < BM / p.TW ? pow2_ceil(p.Ho) : BM / p.TW;
+    p.TN = BM / (p.TW * p.TH);
+    p.tilesW = (p.Wo + p.TW - 1) / p.TW; p.tilesH = (p.Ho + p.TH - 1) / p.TH;
+    const int tilesN = (N + p.TN - 1) / p.TN;
+    p.scale = scale; p.shift = shift; p.resid = resid; p.ldr = ldr; p.act = act; p.slope = slope; p.y = y;
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin_p, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)Win * ldx * 4, (cuuint64_t)Hin * Win * ldx * 4};
+        cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc: activation tensor map rejected (%d)", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S)};
+        cuuint64_t strides[2] = {(cuuint64_t)Cin_p * 4, (cuuint64_t)Cin_p * Cout_p * 4};
+        cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN_MAX, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wpack_tc), dims, strides, box,
+                            es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc: weight tensor map rejected (%d)", (int)r);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) { mk_set_error("mk_conv2d_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(p.tilesW * p.tilesH * tilesN), (unsigned)((Cout_p + BN_MAX - 1) / BN_MAX));
+    k_conv_tc<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+    return mk_check_launch("mk_conv2d_tc");
+}

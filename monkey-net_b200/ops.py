@@ -8,6 +8,8 @@ Internal activation layout: NHWC fp32 `[N][H][W][Cp]`, N = B*D frames, physical 
 of 4 with zero channels.  `Act` carries the tensor plus its channel segments `((logical, padded), ...)` - a concat
 of padded tensors has holes, which the weight packer skips via a physical->logical channel map.
 """
+import os
+
 import torch
 
 from . import lib
@@ -46,6 +48,20 @@ def _zeros(*shape, like):
 
 
 _MAP_CACHE = {}
+
+# Convolution arithmetic: 'fp32' = exact FFMA kernel (parity 1e-5), 'tf32' = tcgen05 tensor-core kernel for the
+# forward and input-gradient convolutions wherever its envelope allows (Cin_p >= 8, Cout_p % 16 == 0, no upsample).
+CONV_MODE = os.environ.get('MONKEY_B200_CONV', 'fp32')
+
+
+def set_conv_mode(mode):
+    global CONV_MODE
+    assert mode in ('fp32', 'tf32')
+    CONV_MODE = mode
+
+
+def _tc_ok(cin_p, cout_p, ups, pool):
+    return CONV_MODE == 'tf32' and not ups and not pool and cin_p >= 8 and cout_p % 16 == 0
 
 
 def _channel_maps(segs, device):
@@ -172,17 +188,24 @@ class _Conv(torch.autograd.Function):
         st = _stream()
         wpack = _empty(R * S * Cp * Cop, like=x)
         bias_p = _empty(Cop, like=x) if bias is not None else None
-        lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop, 0, wpack.data_ptr(),
-                 _ptr(bias), _ptr(bias_p), st)
+        tc = _tc_ok(Cp, Cop, ups, pool)  # tensor-core path: pack mode 2 = [tap][Cout_p][Cin_p] rounded to TF32
+        lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop, 2 if tc else 0,
+                 wpack.data_ptr(), _ptr(bias), _ptr(bias_p), st)
         Hl, Wl = Hin << ups, Win << ups
         Ho, Wo = Hl + 2 * pad - R + 1, Wl + 2 * pad - S + 1
         if pool:
             y = _empty(N, Ho >> 1, Wo >> 1, Cop, like=x)
         else:
             y = _empty(N, Ho, Wo, Cop, like=x)
-        lib.call('mk_conv2d', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, None, _ptr(bias_p),
-                 _ptr(resid), Cop if resid is not None else 0, {None: 0, 'relu': 1, 'sigmoid': 2}[act], 0.0,
-                 y.data_ptr(), Cop, Cop, pool, st)
+        act_code = {None: 0, 'relu': 1, 'sigmoid': 2}[act]
+        if tc:
+            lib.call('mk_conv2d_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, wpack.data_ptr(), R, S, pad, None,
+                     _ptr(bias_p), _ptr(resid), Cop if resid is not None else 0, act_code, 0.0, y.data_ptr(), Cop, Cop,
+                     st)
+        else:
+            lib.call('mk_conv2d', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, None,
+                     _ptr(bias_p), _ptr(resid), Cop if resid is not None else 0, act_code, 0.0, y.data_ptr(), Cop, Cop,
+                     pool, st)
         ctx.cfg = (segs, pad, groups, ups, act, pool, bias is not None, resid is not None)
         ctx.save_for_backward(x, weight, y if act == 'sigmoid' else None)
         return y
@@ -206,13 +229,18 @@ class _Conv(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             wt = _empty(R * S * Cop * Cp, like=x)
-            lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop, 1, wt.data_ptr(),
-                     None, None, st)
+            tc = _tc_ok(Cop, Cp, ups, 0)
+            lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop, 3 if tc else 1,
+                     wt.data_ptr(), None, None, st)
             dx = _empty(N, Hin, Win, Cp, like=x)
             # dgrad = correlation of dy with the flipped/transposed kernel, padding R-1-pad; the transpose of the
             # nearest-x2 upsample is a 2x2 sum, fused as the conv's pooled epilogue
-            lib.call('mk_conv2d', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
-                     R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, 2 if ups else 0, st)
+            if tc:
+                lib.call('mk_conv2d_tc', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, wt.data_ptr(), R, S,
+                         R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, st)
+            else:
+                lib.call('mk_conv2d', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
+                         R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, 2 if ups else 0, st)
         if ctx.needs_input_grad[1]:
             dwp = _empty(R * S * Cp * Cop, like=x)
             lib.call('mk_conv2d_wgrad', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, dy.data_ptr(), Cop, Cop, R, S, pad,
