@@ -53,6 +53,7 @@ int mk_add_channels(const float* src, int lds, float* dst, int ldd, long long np
  * Weight packing: w is the reference parameter (Co, Ci/groups, 1, R, S).  wpack is [R*S][Kin_p][Kout_p].
  *   mode 0 (forward):  Kin = input channels,  Kout = output channels, tap = r*S+s.
  *   mode 1 (dgrad):    Kin = output channels, Kout = input channels,  tap flipped (R-1-r, S-1-s).
+ *   mode 4:            sub-pixel forward pack for the upsampled 3x3 conv, [4 parities][4 taps][Kout_p][Kin_p], TF32.
  *   modes 2 / 3:       modes 0 / 1 in the tensor-core layout [R*S][Kout_p][Kin_p], rounded to TF32 (mk_conv2d_tc).
  * `cin_map[Cin_p]` maps each PHYSICAL input channel to its logical index or -1 (padding / concat holes);
  * physical output channel j is logical j for j < Co, padding otherwise.  Grouped convs are packed block-diagonal. */
@@ -78,14 +79,23 @@ int mk_conv2d(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int u
 /* Tensor-core variant of mk_conv2d for stride-1 convs without upsample/pool: 4-D TMA boxes of the NHWC activation
  * (out-of-bounds zero fill == conv padding) -> 128B-swizzled smem -> tcgen05.mma kind::tf32, TMEM accumulators.
  * wpack_tc = mk_pack_weight mode 2 (forward) / 3 (dgrad): layout [tap][Kout_p][Kin_p], values rounded to TF32.
+ * ups=1 (R=S=3, pad=1 only): conv3x3(nearest-upsample-x2(x)) (util.py:71-88) computed as FOUR 2x2 sub-pixel convs on
+ * the low-resolution grid, one per output parity, with pre-summed taps (mk_pack_weight mode 4:
+ * [parity][2x2 tap][Kout_p][Kin_p]) - 2.25x fewer FLOPs than convolving the upsampled tensor.
  * Needs Cin_p >= 8 and Cout_p % 16 == 0; returns -2 (and touches nothing) when the shape is outside that envelope
  * so the caller can use mk_conv2d. */
-int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc, int R, int S,
-                 int pad, const float* scale, const float* shift, const float* resid, int ldr, int act, float slope,
+int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups, const float* wpack_tc, int R,
+                 int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act, float slope,
                  float* y, int Cout_p, int ldy, void* stream);
 /* dwpack[R*S][Cin_p][Cout_p] = sum over pixels of im2col(x)^T dy  (zero-filled inside). */
 int mk_conv2d_wgrad(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
                     const float* dy, int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream);
+
+/* Tensor-core variant of mk_conv2d_wgrad (no upsample): both GEMM operands are consumed MN-major straight from the
+ * NHWC tensors (tcgen05 a_major = b_major = 1), K = pixels, split over pixel ranges with fp32 atomics.  Same output
+ * layout as mk_conv2d_wgrad.  Needs Cin_p % 16 == 0 and Cout_p % 16 == 0; returns -2 otherwise. */
+int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
+                       int ldy, int R, int S, int pad, float* dwpack, void* stream);
 
 /* ---- normalisation: BatchNorm over (N,D,H,W) (sync_batchnorm/batchnorm.py:48-78 -> F.batch_norm semantics on the
  *      global batch) and InstanceNorm3d (discriminator.py:20) -------------------------------------------------

@@ -431,12 +431,50 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
     wp[i] = v;
 }
 
+// mode 4: sub-pixel pack of a 3x3 kernel applied after a nearest x2 upsample (util.py:84-85).  For output parity
+// (py,px) the conv is a 2x2 conv of the low-resolution input whose taps are sums of the 3x3 taps:
+//   py = 0: rows {0} | {1,2}      py = 1: rows {0,1} | {2}        (same for columns)
+// Layout [parity = py*2+px][tap = r2*2+s2][Cout_p][Cin_p], rounded to TF32 after the sum.
+__global__ void k_pack_weight_ups(const float* __restrict__ w, int Co, int Ci, const int* __restrict__ cin_map,
+                                  int Cin_p, int Cout_p, float* __restrict__ wp, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ci_p = (int)(i % Cin_p);
+    long long t = i / Cin_p;
+    const int co = (int)(t % Cout_p);
+    t /= Cout_p;
+    const int tap = (int)(t & 3), par = (int)(t >> 2);
+    const int py = par >> 1, px = par & 1, r2 = tap >> 1, s2 = tap & 1;
+    const int ci = cin_map ? cin_map[ci_p] : ci_p;
+    float v = 0.f;
+    if (co < Co && ci >= 0 && ci < Ci) {
+        const int r_lo = py == 0 ? (r2 == 0 ? 0 : 1) : (r2 == 0 ? 0 : 2), r_hi = py == 0 ? (r2 == 0 ? 0 : 2) : (r2 == 0 ? 1 : 2);
+        const int s_lo = px == 0 ? (s2 == 0 ? 0 : 1) : (s2 == 0 ? 0 : 2), s_hi = px == 0 ? (s2 == 0 ? 0 : 2) : (s2 == 0 ? 1 : 2);
+        const float* wk = w + ((long long)co * Ci + ci) * 9;
+        for (int r = r_lo; r <= r_hi; ++r)
+            for (int sx = s_lo; sx <= s_hi; ++sx) v += wk[r * 3 + sx];
+    }
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    wp[i] = __uint_as_float(u);
+}
+
 MK_EXPORT int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int groups, const int* cin_map,
                              int Cin_p, int Cout_p, int mode, float* wpack, const float* bias, float* bias_p,
                              void* stream) {
     long long total = (long long)R * S * Cin_p * Cout_p;
     if (total == 0) return 0;
     MK_REQUIRE(total >= Cout_p, "mk_pack_weight: degenerate shape");
+    if (mode == 4) {
+        MK_REQUIRE(R == 3 && S == 3 && groups == 1, "mk_pack_weight mode 4: 3x3 ungrouped kernels only");
+        total = 16LL * Cin_p * Cout_p;
+        k_pack_weight_ups<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Co, Cig, cin_map, Cin_p,
+                                                                                           Cout_p, wpack, total);
+        if (bias_p)  // zero-padded bias copy: the regular kernel with an empty weight range (total = 0)
+            k_pack_weight<<<(unsigned)mk_cdiv(Cout_p, 256), 256, 0, (cudaStream_t)stream>>>(
+                w, Co, Cig, R, S, groups, cin_map, Cin_p, Cout_p, 0, wpack, 0, bias, bias_p);
+        return mk_check_launch("mk_pack_weight(ups)");
+    }
     k_pack_weight<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         w, Co, Cig, R, S, groups, cin_map, Cin_p, Cout_p, mode, wpack, total, bias, bias_p);
     return mk_check_launch("mk_pack_weight");

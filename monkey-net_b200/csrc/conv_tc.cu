@@ -15,9 +15,10 @@
 // Same contract as mk_conv2d (conv.cu) for stride-1 convs without the upsample / pool options.
 #include "common.cuh"
 #include "../../include/monkey_b200.h"
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace {
+using namespace mk_tc;
 
 constexpr int BM = 128;        // output pixels per CTA (UMMA M)
 constexpr int BN_MAX = 128;    // output channels per CTA (UMMA N <= 128)
@@ -30,98 +31,11 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barrier
 
 struct TcP {
     int N, Ho, Wo, Cout_p, ldy, Cin_p, R, S, pad;
+    int ups;  // 1: nearest-x2-upsampled 3x3 conv as four 2x2 sub-pixel convs (grid.z = output parity)
     int TW, TH, TN, tilesW, tilesH;
     const float* scale; const float* shift; const float* resid; int ldr, act; float slope;
     float* y;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    uint32_t spins = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (!done && ++spins > (1u << 26)) __trap();  // a protocol bug must abort, never hang the GPU box
-    }
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-// K-major, 128B-swizzled operand: rows of 128 B, 8-row atoms of 1024 B (SBO), descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc(const void* smem) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);  // start address, 16-byte units
-    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major) = 1
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                            // descriptor version
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
-    uint32_t d = 0;
-    d |= 1u << 4;                  // D = F32
-    d |= 2u << 7;                  // A = TF32
-    d |= 2u << 10;                 // B = TF32
-    d |= (uint32_t)(n >> 3) << 17; // N
-    d |= (uint32_t)(m >> 4) << 24; // M
-    return d;                      // a_major = b_major = 0 (K-major), no negate, dense
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtensorMap tmA,
                                                  const __grid_constant__ CUtensorMap tmB, const TcP p) {
@@ -142,6 +56,11 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     const int n_this = min(BN_MAX, p.Cout_p - cout0);
     const int nchunks = (p.Cin_p + KC - 1) / KC;
     const int niter = p.R * p.S * nchunks;
+    // sub-pixel decomposition of conv3x3(upsample2x(x)): output parity (py,px) is a 2x2 conv of x whose taps are
+    // sums of the 3x3 taps (pre-summed by mk_pack_weight mode 4) with row offsets {-1,0} (py=0) or {0,+1} (py=1)
+    const int py = p.ups ? (int)(blockIdx.z >> 1) : 0, px = p.ups ? (int)(blockIdx.z & 1) : 0;
+    const int pad_h = p.ups ? 1 - py : p.pad, pad_w = p.ups ? 1 - px : p.pad;
+    const int tap0 = p.ups ? (int)blockIdx.z * 4 : 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -174,8 +93,8 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* a = smem + stage * STAGE_BYTES;
                 mbar_expect_tx(&full[stage], STAGE_BYTES);
-                tma_load_4d(a, &tmA, &full[stage], ch * KC, w0 + s - p.pad, h0 + r - p.pad, n0);
-                tma_load_3d(a + A_BYTES, &tmB, &full[stage], ch * KC, cout0, tap);
+                tma_load_4d(a, &tmA, &full[stage], ch * KC, w0 + s - pad_w, h0 + r - pad_h, n0);
+                tma_load_3d(a + A_BYTES, &tmB, &full[stage], ch * KC, cout0, tap0 + tap);
             }
         }
     } else if (warp == 1) {
@@ -209,7 +128,8 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
         const int in_ = row / (p.TW * p.TH);
         const int n = n0 + in_, h = h0 + ih, w = w0 + iw;
         const bool valid = n < p.N && h < p.Ho && w < p.Wo;
-        const long long pix = ((long long)n * p.Ho + h) * p.Wo + w;
+        const long long pix = p.ups ? ((long long)n * (2 * p.Ho) + (2 * h + py)) * (2 * p.Wo) + (2 * w + px)
+                                    : ((long long)n * p.Ho + h) * p.Wo + w;
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int c = 0; c < n_this; c += 16) {
@@ -243,33 +163,11 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-int pow2_ceil(int v) {
-    int p = 1;
-    while (p < v) p <<= 1;
-    return p;
-}
-
 }  // namespace
 
 // Returns 0 on success, -2 if the shape is outside this kernel's envelope (caller uses mk_conv2d instead).
-MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc, int R,
-                           int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
+MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
+                           const float* wpack_tc, int R, int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
                            float slope, float* y, int Cout_p, int ldy, void* stream) {
     if (Cin_p % 4 || ldx % 4 || Cout_p % 16 || ldy % 4 || Cin_p < 8 || (resid && ldr % 4)) {
         mk_set_error("mk_conv2d_tc: unsupported channel configuration");
@@ -278,7 +176,15 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     EncodeTiledFn encode = get_encode();
     MK_REQUIRE(encode != nullptr, "mk_conv2d_tc: cuTensorMapEncodeTiled unavailable");
     TcP p;
-    p.N = N; p.Ho = Hin + 2 * pad - R + 1; p.Wo = Win + 2 * pad - S + 1;
+    p.ups = ups ? 1 : 0;
+    if (p.ups) {
+        MK_REQUIRE(R == 3 && S == 3 && pad == 1, "mk_conv2d_tc: the upsampled path is the 3x3 / pad 1 conv of util.py:71-88");
+        R = S = 2;  // per-parity 2x2 kernels; the GEMM tile walks the LOW-resolution grid
+        pad = 0;
+        p.N = N; p.Ho = Hin; p.Wo = Win;
+    } else {
+        p.N = N; p.Ho = Hin + 2 * pad - R + 1; p.Wo = Win + 2 * pad - S + 1;
+    }
     MK_REQUIRE(p.Ho > 0 && p.Wo > 0, "mk_conv2d_tc: empty output");
     p.Cout_p = Cout_p; p.ldy = ldy; p.Cin_p = Cin_p; p.R = R; p.S = S; p.pad = pad;
     p.TW = pow2_ceil(p.Wo) < 16 ? pow2_ceil(p.Wo) : 16;
@@ -300,7 +206,7 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
         MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc: activation tensor map rejected (%d)", (int)r);
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S)};
+        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S * (p.ups ? 4 : 1))};
         cuuint64_t strides[2] = {(cuuint64_t)Cin_p * 4, (cuuint64_t)Cin_p * Cout_p * 4};
         cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN_MAX, 1};
         cuuint32_t es[3] = {1, 1, 1};
@@ -315,7 +221,7 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
         if (e != cudaSuccess) { mk_set_error("mk_conv2d_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    dim3 grid((unsigned)(p.tilesW * p.tilesH * tilesN), (unsigned)((Cout_p + BN_MAX - 1) / BN_MAX));
+    dim3 grid((unsigned)(p.tilesW * p.tilesH * tilesN), (unsigned)((Cout_p + BN_MAX - 1) / BN_MAX), p.ups ? 4 : 1);
     k_conv_tc<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
     return mk_check_launch("mk_conv2d_tc");
 }

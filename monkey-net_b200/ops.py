@@ -60,8 +60,14 @@ def set_conv_mode(mode):
     CONV_MODE = mode
 
 
-def _tc_ok(cin_p, cout_p, ups, pool):
-    return CONV_MODE == 'tf32' and not ups and not pool and cin_p >= 8 and cout_p % 16 == 0
+def _tc_ok(cin_p, cout_p, ups, pool, k=3, groups=1, for_dgrad=False):
+    """Envelope of mk_conv2d_tc.  The upsampled forward conv runs as four sub-pixel 2x2 convs (3x3 kernels only);
+    the input gradient of an upsampled conv keeps the FFMA kernel (its 2x2 sum-pool epilogue is the upsample transpose)."""
+    if CONV_MODE != 'tf32' or pool or cin_p < 8 or cout_p % 16 != 0:
+        return False
+    if ups:
+        return (not for_dgrad) and k == 3 and groups == 1
+    return True
 
 
 def _channel_maps(segs, device):
@@ -188,9 +194,12 @@ class _Conv(torch.autograd.Function):
         st = _stream()
         wpack = _empty(R * S * Cp * Cop, like=x)
         bias_p = _empty(Cop, like=x) if bias is not None else None
-        tc = _tc_ok(Cp, Cop, ups, pool)  # tensor-core path: pack mode 2 = [tap][Cout_p][Cin_p] rounded to TF32
-        lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop, 2 if tc else 0,
-                 wpack.data_ptr(), _ptr(bias), _ptr(bias_p), st)
+        # tensor-core path: pack mode 2 = [tap][Cout_p][Cin_p] (TF32), mode 4 = sub-pixel pack of the upsampled conv
+        tc = _tc_ok(Cp, Cop, ups, pool, R, groups)
+        if tc and ups:
+            wpack = _empty(16 * Cp * Cop, like=x)
+        lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop,
+                 (4 if ups else 2) if tc else 0, wpack.data_ptr(), _ptr(bias), _ptr(bias_p), st)
         Hl, Wl = Hin << ups, Win << ups
         Ho, Wo = Hl + 2 * pad - R + 1, Wl + 2 * pad - S + 1
         if pool:
@@ -199,7 +208,7 @@ class _Conv(torch.autograd.Function):
             y = _empty(N, Ho, Wo, Cop, like=x)
         act_code = {None: 0, 'relu': 1, 'sigmoid': 2}[act]
         if tc:
-            lib.call('mk_conv2d_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, wpack.data_ptr(), R, S, pad, None,
+            lib.call('mk_conv2d_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, None,
                      _ptr(bias_p), _ptr(resid), Cop if resid is not None else 0, act_code, 0.0, y.data_ptr(), Cop, Cop,
                      st)
         else:
@@ -229,22 +238,26 @@ class _Conv(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             wt = _empty(R * S * Cop * Cp, like=x)
-            tc = _tc_ok(Cop, Cp, ups, 0)
+            tc = _tc_ok(Cop, Cp, ups, 0, R, groups, for_dgrad=True)
             lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop, 3 if tc else 1,
                      wt.data_ptr(), None, None, st)
             dx = _empty(N, Hin, Win, Cp, like=x)
             # dgrad = correlation of dy with the flipped/transposed kernel, padding R-1-pad; the transpose of the
             # nearest-x2 upsample is a 2x2 sum, fused as the conv's pooled epilogue
             if tc:
-                lib.call('mk_conv2d_tc', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, wt.data_ptr(), R, S,
+                lib.call('mk_conv2d_tc', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
                          R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, st)
             else:
                 lib.call('mk_conv2d', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
                          R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, 2 if ups else 0, st)
         if ctx.needs_input_grad[1]:
             dwp = _empty(R * S * Cp * Cop, like=x)
-            lib.call('mk_conv2d_wgrad', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, dy.data_ptr(), Cop, Cop, R, S, pad,
-                     dwp.data_ptr(), st)
+            if CONV_MODE == 'tf32' and not ups and Cp % 16 == 0 and Cop % 16 == 0:
+                lib.call('mk_conv2d_wgrad_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, dy.data_ptr(), Cop, Cop, R, S, pad,
+                         dwp.data_ptr(), st)
+            else:
+                lib.call('mk_conv2d_wgrad', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, dy.data_ptr(), Cop, Cop, R, S, pad,
+                         dwp.data_ptr(), st)
             dw = torch.empty_like(weight)
             lib.call('mk_unpack_wgrad', dwp.data_ptr(), Co, Cig, R, S, groups, _ptr(cinv), Cp, Cop, dw.data_ptr(), st)
         if has_bias and ctx.needs_input_grad[2]:

@@ -46,12 +46,94 @@ def test_conv_tc_matches_fp32_kernel(cin, cout, k, pad, H, W, N, resid, act):
     rp = r.data_ptr() if resid else None
     lib.call('mk_conv2d', x.data_ptr(), N, H, W, cin, cin, 0, wp.data_ptr(), k, k, pad, None, bp.data_ptr(), rp,
              cout if resid else 0, act, 0.0, y0.data_ptr(), cout, cout, 0, st)
-    lib.call('mk_conv2d_tc', x.data_ptr(), N, H, W, cin, cin, wt.data_ptr(), k, k, pad, None, bp.data_ptr(), rp,
+    lib.call('mk_conv2d_tc', x.data_ptr(), N, H, W, cin, cin, 0, wt.data_ptr(), k, k, pad, None, bp.data_ptr(), rp,
              cout if resid else 0, act, 0.0, y1.data_ptr(), cout, cout, st)
     torch.cuda.synchronize()
     assert not torch.isnan(y1).any(), 'tensor-core kernel left outputs unwritten'
     err = float((y0 - y1).abs().max()) / (float(y0.abs().max()) + 1e-12)
     assert err < 2e-3, err
+
+
+@pytest.mark.parametrize('cin,cout,H,W,N', [(64, 32, 16, 16, 2), (128, 64, 4, 4, 4), (40, 16, 9, 5, 3), (256, 128, 2, 2, 8)])
+def test_conv_tc_upsampled_subpixel(cin, cout, H, W, N):
+    """conv3x3(nearest_x2(x)) as four 2x2 sub-pixel convs on tensor cores == the fp32 kernel's on-the-fly upsample."""
+    from monkey_net_b200 import lib
+    torch.manual_seed(cin + H)
+    dev = torch.device('cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(N, H, W, cin, device=dev)
+    w = torch.randn(cout, cin, 1, 3, 3, device=dev) / (cin * 9) ** 0.5
+    b = torch.randn(cout, device=dev)
+    wp, wt = torch.empty(9 * cin * cout, device=dev), torch.empty(16 * cin * cout, device=dev)
+    bp, bp2 = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
+    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, 3, 3, 1, None, cin, cout, 0, wp.data_ptr(), b.data_ptr(),
+             bp.data_ptr(), st)
+    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, 3, 3, 1, None, cin, cout, 4, wt.data_ptr(), b.data_ptr(),
+             bp2.data_ptr(), st)
+    y0 = torch.empty(N, 2 * H, 2 * W, cout, device=dev)
+    y1 = torch.full((N, 2 * H, 2 * W, cout), float('nan'), device=dev)
+    lib.call('mk_conv2d', x.data_ptr(), N, H, W, cin, cin, 1, wp.data_ptr(), 3, 3, 1, None, bp.data_ptr(), None, 0, 0,
+             0.0, y0.data_ptr(), cout, cout, 0, st)
+    lib.call('mk_conv2d_tc', x.data_ptr(), N, H, W, cin, cin, 1, wt.data_ptr(), 3, 3, 1, None, bp2.data_ptr(), None, 0,
+             0, 0.0, y1.data_ptr(), cout, cout, st)
+    torch.cuda.synchronize()
+    assert torch.equal(bp, bp2)
+    assert not torch.isnan(y1).any()
+    err = float((y0 - y1).abs().max()) / (float(y0.abs().max()) + 1e-12)
+    assert err < 2e-3, err
+
+
+@pytest.mark.parametrize('cin,cout,k,pad,H,W,N', [(32, 64, 3, 1, 16, 16, 4), (64, 128, 3, 1, 32, 32, 2),
+                                                   (16, 32, 3, 1, 64, 64, 2), (48, 144, 3, 1, 13, 9, 3),
+                                                   (256, 256, 3, 1, 4, 4, 8), (512, 128, 3, 1, 2, 2, 32),
+                                                   (64, 128, 4, 0, 29, 29, 2), (48, 16, 1, 0, 16, 16, 2),
+                                                   (160, 32, 3, 1, 8, 8, 4)])
+def test_wgrad_tc_matches_fp32_kernel(cin, cout, k, pad, H, W, N):
+    from monkey_net_b200 import lib
+    torch.manual_seed(cin + cout)
+    dev = torch.device('cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    x = torch.randn(N, H, W, cin, device=dev)
+    dy = torch.randn(N, Ho, Wo, cout, device=dev)
+    d0 = torch.empty(k * k * cin * cout, device=dev)
+    d1 = torch.full((k * k * cin * cout,), float('nan'), device=dev)
+    lib.call('mk_conv2d_wgrad', x.data_ptr(), N, H, W, cin, cin, 0, dy.data_ptr(), cout, cout, k, k, pad, d0.data_ptr(), st)
+    lib.call('mk_conv2d_wgrad_tc', x.data_ptr(), N, H, W, cin, cin, dy.data_ptr(), cout, cout, k, k, pad, d1.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert not torch.isnan(d1).any()
+    err = float((d0 - d1).abs().max()) / (float(d0.abs().max()) + 1e-12)
+    assert err < 2e-3, err
+
+
+def test_train_step_tf32_mode_gradients():
+    """G-step gradients with every conv (fwd, dgrad, wgrad) on tensor cores vs the fp32 oracle: TF32-level agreement."""
+    from monkey_net_b200 import ops, train_step
+    from oracle import monkey_oracle as mo
+    import test_gpu_2_modules as t2
+    cfg = helpers.load_config('shapes')
+    (gen, disc, kp), (og, od, ok), x = t2._pair(cfg, 64, 2)
+    tp = cfg['train_params']
+    for m in (gen, disc, kp, og, od, ok):
+        m.train()
+    out = mo.generator_full(ok, og, od, tp, x)
+    sum(v.mean() for v in out[:-2]).backward()
+    ops.set_conv_mode('tf32')
+    try:
+        pout = train_step.GeneratorFullModel(kp, gen, disc, tp)({k: v.cuda() for k, v in x.items()})
+        sum(v.mean() for v in pout[:-2]).backward()
+    finally:
+        ops.set_conv_mode('fp32')
+    worst = 0.0
+    for (n1, p1), (n2, p2) in zip(list(gen.named_parameters()) + list(kp.named_parameters()),
+                                  list(og.named_parameters()) + list(ok.named_parameters())):
+        if p2.grad is None or helpers.structurally_zero_grad(n1):
+            continue
+        a, b = p1.grad.detach().cpu().flatten(), p2.grad.flatten()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+        worst = max(worst, 1 - cos)
+        assert cos > 0.999, (n1, cos)
+    print('tf32 train step: worst 1-cos(grad) = %.2e' % worst)
 
 
 def test_conv_tc_rejects_unsupported_shapes_without_touching_output():
@@ -61,7 +143,7 @@ def test_conv_tc_rejects_unsupported_shapes_without_touching_output():
     y = torch.zeros(1, 8, 8, 16, device=dev)
     w = torch.zeros(9 * 4 * 16, device=dev)
     with pytest.raises(RuntimeError, match='unsupported'):
-        lib.call('mk_conv2d_tc', x.data_ptr(), 1, 8, 8, 4, 4, w.data_ptr(), 3, 3, 1, None, None, None, 0, 0, 0.0,
+        lib.call('mk_conv2d_tc', x.data_ptr(), 1, 8, 8, 4, 4, 0, w.data_ptr(), 3, 3, 1, None, None, None, 0, 0, 0.0,
                  y.data_ptr(), 16, 16, torch.cuda.current_stream().cuda_stream)
 
 
