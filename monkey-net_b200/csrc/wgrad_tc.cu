@@ -5,8 +5,9 @@
 // directly (a_major = b_major = 1 in the instruction descriptor), so no transposed copies of the activations exist:
 //   * A stage = four 4-D TMA boxes {32 co, TW, TH, TN} of dY (32 pixels each), B stage = up to four boxes
 //     {32 ci, TW, TH, TN} of X shifted by the filter tap; out-of-bounds pixels are zero-filled = conv padding.
-//     Each box is [32 pixels][128 B] with the 128B swizzle = one MN block of the canonical MN-major layout
-//     ((8,n),(8,k)):((1,LBO),(8,SBO)) with LBO = box size (4096 B), SBO = 1024 B (8 pixel rows).
+//     Each box is [32 pixels][128 B] in the 128B swizzle with 32-byte atoms (TMA SWIZZLE_128B_ATOM_32B ==
+//     UMMA SWIZZLE_128B_BASE32B, the only MN-major layout 32-bit operands may use) = one MN block of the
+//     canonical layout ((8,n),(4,k)) with LBO = box size (4096 B), SBO = 512 B (4 pixel rows).
 //   * 4 x tcgen05.mma.kind::tf32 (K = 8 pixels each) per stage; accumulator [128 co][<=128 ci] fp32 in TMEM.
 //   * grid = (co tiles, taps x ci tiles, pixel splits); splits combine with fp32 atomics (red) into the packed
 //     gradient, whose layout [tap][Cin_p][Cout_p] makes the epilogue's per-column writes coalesced across lanes.
@@ -32,9 +33,9 @@ __device__ __forceinline__ uint64_t umma_desc_mn(const void* smem) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_u32(smem) & 0x3FFFF) >> 4);
     d |= (uint64_t)(BOX_BYTES >> 4) << 16;  // LBO: next 32-channel MN block
-    d |= (uint64_t)(1024 >> 4) << 32;       // SBO: next group of 8 pixel rows
+    d |= (uint64_t)(512 >> 4) << 32;        // SBO: next group of 4 pixel rows (the 32B-atom swizzle repeats every 4)
     d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    d |= (uint64_t)1 << 61;                 // SWIZZLE_128B_BASE32B - the only MN-major layout tf32 operands may use
     return d;
 }
 
@@ -177,7 +178,7 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
         cuuint64_t dims[4] = {(cuuint64_t)Cout_p, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)p.Wo * ldy * 4, (cuuint64_t)p.Ho * p.Wo * ldy * 4};
         CUresult rc = encode(&tmDy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(dy), dims, strides, box, es,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MK_REQUIRE(rc == CUDA_SUCCESS, "mk_conv2d_wgrad_tc: dy tensor map rejected (%d)", (int)rc);
     }
@@ -185,7 +186,7 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
         cuuint64_t dims[4] = {(cuuint64_t)Cin_p, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)Win * ldx * 4, (cuuint64_t)Hin * Win * ldx * 4};
         CUresult rc = encode(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MK_REQUIRE(rc == CUDA_SUCCESS, "mk_conv2d_wgrad_tc: x tensor map rejected (%d)", (int)rc);
     }
