@@ -82,8 +82,8 @@ int mk_conv2d(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int u
  * ups=1 (R=S=3, pad=1 only): conv3x3(nearest-upsample-x2(x)) (util.py:71-88) computed as FOUR 2x2 sub-pixel convs on
  * the low-resolution grid, one per output parity, with pre-summed taps (mk_pack_weight mode 4:
  * [parity][2x2 tap][Kout_p][Kin_p]) - 2.25x fewer FLOPs than convolving the upsampled tensor.
- * Needs Cin_p >= 8 and Cout_p % 16 == 0; returns -2 (and touches nothing) when the shape is outside that envelope
- * so the caller can use mk_conv2d. */
+ * Any channel counts that are multiples of 4 (ragged counts ride on the TMA zero fill); returns -2 (and touches
+ * nothing) for unaligned strides so the caller can use mk_conv2d. */
 int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups, const float* wpack_tc, int R,
                  int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act, float slope,
                  float* y, int Cout_p, int ldy, void* stream);
@@ -93,7 +93,7 @@ int mk_conv2d_wgrad(const float* x, int N, int Hin, int Win, int Cin_p, int ldx,
 
 /* Tensor-core variant of mk_conv2d_wgrad (no upsample): both GEMM operands are consumed MN-major straight from the
  * NHWC tensors (tcgen05 a_major = b_major = 1), K = pixels, split over pixel ranges with fp32 atomics.  Same output
- * layout as mk_conv2d_wgrad.  Needs Cin_p % 16 == 0 and Cout_p % 16 == 0; returns -2 otherwise. */
+ * layout as mk_conv2d_wgrad.  Channel counts must be multiples of 4; returns -2 otherwise. */
 int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
                        int ldy, int R, int S, int pad, float* dwpack, void* stream);
 

@@ -100,3 +100,29 @@ __device__ __forceinline__ void linear_src(int dst, int in, int out, int& i0, in
     i1 = i0 + (i0 < in - 1 ? 1 : 0);
     l1 = s - (float)i0;
 }
+
+// ---------------------------------------------------------------------------------------------- index arithmetic
+// The elementwise / gather kernels decode (n, h, w, channel-vector) from a flat thread index.  64-bit div/mod costs
+// ~100 SASS instructions each on sm_100 and made those "HBM-bound" kernels issue-bound (profiles/r1: 45 % SM busy at
+// 14 % DRAM).  All extents here are < 2^31, so the index math is 32-bit, and divisions by power-of-two extents
+// (every channel count and resolution the configs use) are shifts.
+struct FastDiv {
+    unsigned d;
+    int sh;  // >= 0: d == 1 << sh
+};
+static inline FastDiv make_fastdiv(long long d) {
+    FastDiv f;
+    f.d = (unsigned)d;
+    f.sh = -1;
+    if (d > 0 && (d & (d - 1)) == 0) {
+        f.sh = 0;
+        while ((1LL << f.sh) < d) ++f.sh;
+    }
+    return f;
+}
+// q = n / f.d, r = n % f.d
+__device__ __forceinline__ unsigned fd_divmod(unsigned n, const FastDiv f, unsigned& r) {
+    unsigned q = f.sh >= 0 ? n >> f.sh : n / f.d;
+    r = n - q * f.d;
+    return q;
+}

@@ -10,8 +10,8 @@
 // * warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane, tcgen05.mma, commit -> frees the
 //   smem stage), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld 32x32b -> registers -> affine, residual,
 //   activation -> 128-bit stores).  smem ring of STAGES stages with full/empty mbarriers; accumulator handed over
-//   through a tmem_full mbarrier.  3 x 32 KB stages keep two CTAs resident per SM, so one CTA's epilogue overlaps
-//   the other's MMA stream.
+//   through a tmem_full mbarrier.  The ring takes ~200 KB (6-8 stages): at these sizes the K loop is bound by the
+//   TMA round trip, not by the MMA issue rate, so depth beats a second resident CTA.
 // Same contract as mk_conv2d (conv.cu) for stride-1 convs without the upsample / pool options.
 #include "common.cuh"
 #include "../../include/monkey_b200.h"
@@ -23,16 +23,17 @@ using namespace mk_tc;
 constexpr int BM = 128;        // output pixels per CTA (UMMA M)
 constexpr int BN_MAX = 128;    // output channels per CTA (UMMA N <= 128)
 constexpr int KC = 32;         // fp32 channels per stage = 128 bytes = one swizzle row
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 8;   // the ring is as deep as ~200 KB of shared memory allows: the K loop of these convs is
+                                // TMA-latency bound (~1 us round trip vs ~0.13 us of MMA per stage), not MMA bound
 constexpr int A_BYTES = BM * KC * 4;
-constexpr int B_BYTES = BN_MAX * KC * 4;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_MAX = 227 * 1024;
 
 struct TcP {
     int N, Ho, Wo, Cout_p, ldy, Cin_p, R, S, pad;
     int ups;  // 1: nearest-x2-upsampled 3x3 conv as four 2x2 sub-pixel convs (grid.z = output parity)
     int TW, TH, TN, tilesW, tilesH;
+    int nstages, stage_bytes;  // smem ring: stage = A tile (16 KB) + B tile (b_rows x 128 B)
     const float* scale; const float* shift; const float* resid; int ldr, act; float slope;
     float* y;
 };
@@ -41,9 +42,10 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                                                  const __grid_constant__ CUtensorMap tmB, const TcP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int STAGES = p.nstages, STAGE_BYTES = p.stage_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tmem_full = empty + MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
-        const uint32_t idesc = umma_idesc_tf32(BM, n_this);
+        const uint32_t idesc = umma_idesc_tf32(BM, (n_this + 15) & ~15);  // rows beyond Cout_p are TMA zero fill
         for (int it = 0; it < niter; ++it) {
             const int stage = it % STAGES;
             const uint32_t phase = (it / STAGES) & 1;
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             const int co = cout0 + c;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
+                if (c + j >= n_this) break;  // ragged Cout_p (multiple of 4, not of 16)
                 float4 sc = p.scale ? ldg4(p.scale + co + j) : make_float4(1.f, 1.f, 1.f, 1.f);
                 float4 sh = p.shift ? ldg4(p.shift + co + j) : f4zero();
                 float4 o = make_float4(fmaf(v[j], sc.x, sh.x), fmaf(v[j + 1], sc.y, sh.y), fmaf(v[j + 2], sc.z, sh.z),
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
 MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
                            const float* wpack_tc, int R, int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
                            float slope, float* y, int Cout_p, int ldy, void* stream) {
-    if (Cin_p % 4 || ldx % 4 || Cout_p % 16 || ldy % 4 || Cin_p < 8 || (resid && ldr % 4)) {
+    if (Cin_p % 4 || ldx % 4 || Cout_p % 4 || ldy % 4 || (resid && ldr % 4)) {
         mk_set_error("mk_conv2d_tc: unsupported channel configuration");
         return -2;
     }
@@ -194,6 +197,10 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     const int tilesN = (N + p.TN - 1) / p.TN;
     p.scale = scale; p.shift = shift; p.resid = resid; p.ldr = ldr; p.act = act; p.slope = slope; p.y = y;
 
+    const int b_rows = Cout_p < BN_MAX ? (Cout_p + 15) & ~15 : BN_MAX;  // weight rows per stage = UMMA N
+    p.stage_bytes = A_BYTES + b_rows * KC * 4;
+    p.nstages = SMEM_BUDGET / p.stage_bytes < MAX_STAGES ? SMEM_BUDGET / p.stage_bytes : MAX_STAGES;
+    const int smem_bytes = p.nstages * p.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin_p, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
@@ -208,7 +215,7 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     {
         cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S * (p.ups ? 4 : 1))};
         cuuint64_t strides[2] = {(cuuint64_t)Cin_p * 4, (cuuint64_t)Cin_p * Cout_p * 4};
-        cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)BN_MAX, 1};
+        cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)b_rows, 1};
         cuuint32_t es[3] = {1, 1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wpack_tc), dims, strides, box,
                             es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -217,11 +224,11 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) { mk_set_error("mk_conv2d_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
     dim3 grid((unsigned)(p.tilesW * p.tilesH * tilesN), (unsigned)((Cout_p + BN_MAX - 1) / BN_MAX), p.ups ? 4 : 1);
-    k_conv_tc<<<grid, 256, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, p);
+    k_conv_tc<<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
     return mk_check_launch("mk_conv2d_tc");
 }

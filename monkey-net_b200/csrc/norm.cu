@@ -207,34 +207,33 @@ __device__ __forceinline__ float4 affine_act(float4 v, float4 sc, float4 sh, flo
 __global__ void __launch_bounds__(256) k_norm_apply(const float* __restrict__ x, int ldx, int N, int H, int W, int Cp,
                                                     const float* __restrict__ params, int per_frame, float slope,
                                                     int pool, float* __restrict__ out, int ldo, int Ho, int Wo,
-                                                    long long total) {
-    const int cv = Cp >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cv) * 4;
-        const long long op = i / cv;
-        const int wo = (int)(op % Wo);
-        const long long t = op / Wo;
-        const int ho = (int)(t % Ho);
-        const long long n = t / Ho;
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = f4zero();
-        if (params) {
-            const float* pr = params + (per_frame ? n : 0) * 4 * Cp;
-            sc = ldg4(pr + 2 * Cp + c);
-            sh = ldg4(pr + 3 * Cp + c);
-        }
-        float4 r;
-        if (pool) {
-            const float* b = x + ((n * H + 2 * ho) * W + 2 * wo) * ldx + c;
-            r = affine_act(ldg4(b), sc, sh, slope) + affine_act(ldg4(b + ldx), sc, sh, slope) +
-                affine_act(ldg4(b + (long long)W * ldx), sc, sh, slope) +
-                affine_act(ldg4(b + (long long)W * ldx + ldx), sc, sh, slope);
-            r = r * 0.25f;
-        } else {
-            r = affine_act(ldg4(x + op * ldx + c), sc, sh, slope);
-        }
-        st4(out + op * ldo + c, r);
+                                                    long long total, const FastDiv fcv, const FastDiv fwo,
+                                                    const FastDiv fho) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;  // one (output pixel, float4) per thread, 32-bit index math
+    if (i >= (unsigned)total) return;
+    unsigned cq, wo, ho;
+    const unsigned op = fd_divmod(i, fcv, cq);
+    const unsigned t = fd_divmod(op, fwo, wo);
+    const unsigned n = fd_divmod(t, fho, ho);
+    const int c = (int)cq * 4;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = f4zero();
+    if (params) {
+        const float* pr = params + (long long)(per_frame ? n : 0) * 4 * Cp;
+        sc = ldg4(pr + 2 * Cp + c);
+        sh = ldg4(pr + 3 * Cp + c);
     }
+    float4 r;
+    if (pool) {
+        const float* b = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * ldx + c;
+        const float4 v0 = ldg4(b), v1 = ldg4(b + ldx), v2 = ldg4(b + (long long)W * ldx),
+                     v3 = ldg4(b + (long long)W * ldx + ldx);
+        r = affine_act(v0, sc, sh, slope) + affine_act(v1, sc, sh, slope) + affine_act(v2, sc, sh, slope) +
+            affine_act(v3, sc, sh, slope);
+        r = r * 0.25f;
+    } else {
+        r = affine_act(ldg4(x + (long long)op * ldx + c), sc, sh, slope);
+    }
+    st4(out + (long long)op * ldo + c, r);
 }
 
 MK_EXPORT int mk_norm_apply(const float* x, int ldx, int N, int H, int W, int Cp, const float* params, int per_frame,
@@ -243,11 +242,10 @@ MK_EXPORT int mk_norm_apply(const float* x, int ldx, int N, int H, int W, int Cp
     const int Ho = pool ? H >> 1 : H, Wo = pool ? W >> 1 : W;
     const long long total = (long long)N * Ho * Wo * (Cp / 4);
     if (total == 0) return 0;
-    long long blocks = mk_cdiv(total, 256);
-    const long long cap = 16LL * mk_num_sms();
-    if (blocks > cap) blocks = cap;
-    k_norm_apply<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, N, H, W, Cp, params, per_frame, slope, pool,
-                                                                     out, ldo, Ho, Wo, total);
+    MK_REQUIRE(total < (1LL << 31), "mk_norm_apply: more than 2^31 work items");
+    k_norm_apply<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, ldx, N, H, W, Cp, params, per_frame, slope, pool, out, ldo, Ho, Wo, total, make_fastdiv(Cp / 4),
+        make_fastdiv(Wo), make_fastdiv(Ho));
     return mk_check_launch("mk_norm_apply");
 }
 
@@ -258,29 +256,29 @@ __global__ void __launch_bounds__(256) k_norm_bwd_apply(const float* __restrict_
                                                         const float* __restrict__ sums, float inv_count,
                                                         int per_frame, int normed, float slope, int pool,
                                                         float* __restrict__ dx, int lddx, int Hp, int Wp,
-                                                        long long total) {
-    const int cv = Cp >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cv) * 4;
-        const long long pix = i / cv;
-        const int w = (int)(pix % W);
-        const long long t = pix / W;
-        const int h = (int)(t % H);
-        const long long n = t / H;
+                                                        long long total, const FastDiv fcv, const FastDiv fw,
+                                                        const FastDiv fh) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= (unsigned)total) return;
+    {
+        unsigned cq, wq, hq;
+        const unsigned pix = fd_divmod(i, fcv, cq);
+        const unsigned t = fd_divmod(pix, fw, wq);
+        const unsigned n = fd_divmod(t, fh, hq);
+        const int c = (int)cq * 4, w = (int)wq, h = (int)hq;
         const long long g = per_frame ? n : 0;
         float4 mean = f4zero(), invstd = f4zero(), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = f4zero();
         if (params) {
             const float* pr = params + g * 4 * Cp;
             mean = ldg4(pr + c); invstd = ldg4(pr + Cp + c); sc = ldg4(pr + 2 * Cp + c); sh = ldg4(pr + 3 * Cp + c);
         }
-        const float4 v = ldg4(x + pix * ldx + c);
+        const float4 v = ldg4(x + (long long)pix * ldx + c);
         float4 d;
         if (pool) {
             const int hp = h >> 1, wp = w >> 1;
-            d = (hp < Hp && wp < Wp) ? ldg4(dout + ((n * Hp + hp) * Wp + wp) * ldd + c) * 0.25f : f4zero();
+            d = (hp < Hp && wp < Wp) ? ldg4(dout + (((long long)n * Hp + hp) * Wp + wp) * ldd + c) * 0.25f : f4zero();
         } else {
-            d = ldg4(dout + pix * ldd + c);
+            d = ldg4(dout + (long long)pix * ldd + c);
         }
         if (slope >= 0.f) {
             float4 z = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z),
@@ -299,7 +297,7 @@ __global__ void __launch_bounds__(256) k_norm_bwd_apply(const float* __restrict_
         } else {
             r = d * sc;
         }
-        st4(dx + pix * lddx + c, r);
+        st4(dx + (long long)pix * lddx + c, r);
     }
 }
 
@@ -310,11 +308,9 @@ MK_EXPORT int mk_norm_bwd_apply(const float* x, int ldx, const float* dout, int 
     MK_REQUIRE(!normed || (params && sums), "mk_norm_bwd_apply: normed needs params and sums");
     const long long total = (long long)N * H * W * (Cp / 4);
     if (total == 0) return 0;
-    long long blocks = mk_cdiv(total, 256);
-    const long long cap = 16LL * mk_num_sms();
-    if (blocks > cap) blocks = cap;
-    k_norm_bwd_apply<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+    MK_REQUIRE(total < (1LL << 31), "mk_norm_bwd_apply: more than 2^31 work items");
+    k_norm_bwd_apply<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         x, ldx, dout, ldd, N, H, W, Cp, params, sums, (float)(1.0 / count), per_frame, normed, slope, pool, dx, lddx,
-        pool ? H >> 1 : H, pool ? W >> 1 : W, total);
+        pool ? H >> 1 : H, pool ? W >> 1 : W, total, make_fastdiv(Cp / 4), make_fastdiv(W), make_fastdiv(H));
     return mk_check_launch("mk_norm_bwd_apply");
 }

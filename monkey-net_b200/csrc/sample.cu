@@ -54,57 +54,33 @@ __device__ __forceinline__ Tap make_tap(float2 g, int h, int w) {
 
 __global__ void __launch_bounds__(256) k_grid_sample_fwd(const float* __restrict__ inp, int h, int w, int cv, int ld,
                                                          const float* __restrict__ deform, int d, int h0, int w0,
-                                                         int mode, float* __restrict__ out, int ldo, long long total) {
-    // UNR independent items per thread: all grid fetches first, then all 4*UNR tap loads, then the blends - 16 128-bit
-    // loads in flight per thread, which is what an HBM-latency-bound gather needs (one item at a time ran at ~25 %
-    // of the HBM roofline, profiles/r1).
-    constexpr int UNR = 4;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * UNR) {
-        float4 v[UNR][4];
-        float wgt[UNR][4];
-        long long oidx[UNR];
-        float2 g[UNR];
-        int cc[UNR], hh[UNR], ww[UNR];
-        long long nn[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const long long i = i0 + u * stride;
-            const bool live = i < total;
-            const long long ii = live ? i : 0;
-            cc[u] = (int)(ii % cv) * 4;
-            const long long op = ii / cv;
-            ww[u] = (int)(op % w);
-            const long long t = op / w;
-            hh[u] = (int)(t % h);
-            nn[u] = t / h;
-            oidx[u] = live ? op * ldo + cc[u] : -1;
-            g[u] = fetch_grid(deform, nn[u], h0, w0, hh[u], ww[u], h, w, mode);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const Tap tp = make_tap(g[u], h, w);
-            const float* src = inp + (nn[u] / d) * (long long)h * w * ld + cc[u];
-            const bool xin0 = tp.x0 >= 0 && tp.x0 < w, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < w;
-            const bool yin0 = tp.y0 >= 0 && tp.y0 < h, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < h;
-            const float wx0 = 1.f - tp.wx1, wy0 = 1.f - tp.wy1;
-            // ATen order: nw, ne, sw, se
-            wgt[u][0] = wx0 * wy0; wgt[u][1] = tp.wx1 * wy0; wgt[u][2] = wx0 * tp.wy1; wgt[u][3] = tp.wx1 * tp.wy1;
-            v[u][0] = (yin0 && xin0) ? ldg4(src + ((long long)tp.y0 * w + tp.x0) * ld) : f4zero();
-            v[u][1] = (yin0 && xin1) ? ldg4(src + ((long long)tp.y0 * w + tp.x0 + 1) * ld) : f4zero();
-            v[u][2] = (yin1 && xin0) ? ldg4(src + ((long long)(tp.y0 + 1) * w + tp.x0) * ld) : f4zero();
-            v[u][3] = (yin1 && xin1) ? ldg4(src + ((long long)(tp.y0 + 1) * w + tp.x0 + 1) * ld) : f4zero();
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            float4 acc = f4zero();
-            fma4(acc, v[u][0], wgt[u][0]);
-            fma4(acc, v[u][1], wgt[u][1]);
-            fma4(acc, v[u][2], wgt[u][2]);
-            fma4(acc, v[u][3], wgt[u][3]);
-            if (oidx[u] >= 0) st4(out + oidx[u], acc);
-        }
-    }
+                                                         int mode, float* __restrict__ out, int ldo, long long total,
+                                                         const FastDiv fcv, const FastDiv fw, const FastDiv fh) {
+    // one item (pixel, float4 of channels) per thread, 32-bit index math (see FastDiv): occupancy, not per-thread
+    // unrolling, supplies the memory-level parallelism here - a 4-item unroll measured 13 % slower (profiles/r1)
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= (unsigned)total) return;
+    unsigned cq, wo, ho;
+    const unsigned op = fd_divmod(i, fcv, cq);
+    const unsigned t = fd_divmod(op, fw, wo);
+    const unsigned n = fd_divmod(t, fh, ho);
+    const int c = (int)cq * 4;
+    const Tap tp = make_tap(fetch_grid(deform, n, h0, w0, (int)ho, (int)wo, h, w, mode), h, w);
+    const float* src = inp + (long long)(n / (unsigned)d) * h * w * ld + c;
+    const bool xin0 = tp.x0 >= 0 && tp.x0 < w, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < w;
+    const bool yin0 = tp.y0 >= 0 && tp.y0 < h, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < h;
+    const float wx0 = 1.f - tp.wx1, wy0 = 1.f - tp.wy1;
+    // issue the four tap loads before blending (ATen order: nw, ne, sw, se)
+    const float4 v0 = (yin0 && xin0) ? ldg4(src + (tp.y0 * w + tp.x0) * (long long)ld) : f4zero();
+    const float4 v1 = (yin0 && xin1) ? ldg4(src + (tp.y0 * w + tp.x0 + 1) * (long long)ld) : f4zero();
+    const float4 v2 = (yin1 && xin0) ? ldg4(src + ((tp.y0 + 1) * w + tp.x0) * (long long)ld) : f4zero();
+    const float4 v3 = (yin1 && xin1) ? ldg4(src + ((tp.y0 + 1) * w + tp.x0 + 1) * (long long)ld) : f4zero();
+    float4 acc = f4zero();
+    fma4(acc, v0, wx0 * wy0);
+    fma4(acc, v1, tp.wx1 * wy0);
+    fma4(acc, v2, wx0 * tp.wy1);
+    fma4(acc, v3, tp.wx1 * tp.wy1);
+    st4(out + (long long)op * ldo + c, acc);
 }
 
 MK_EXPORT int mk_grid_sample_fwd(const float* inp, int B, int h, int w, int Cp, int ld, const float* deform, int d,
@@ -112,11 +88,11 @@ MK_EXPORT int mk_grid_sample_fwd(const float* inp, int B, int h, int w, int Cp, 
     MK_REQUIRE(Cp % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0, "mk_grid_sample_fwd: channels must be x4");
     const long long total = (long long)B * d * h * w * (Cp / 4);
     if (total == 0) return 0;
-    long long blocks = mk_cdiv(total, 256 * 4);  // 4 items per thread per loop trip
-    const long long cap = 16LL * mk_num_sms();
-    if (blocks > cap) blocks = cap;
+    MK_REQUIRE(total < (1LL << 31), "mk_grid_sample_fwd: more than 2^31 work items");
+    const long long blocks = mk_cdiv(total, 256);
     k_grid_sample_fwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inp, h, w, Cp / 4, ld, deform, d, h0, w0, mode,
-                                                                          out, ldo, total);
+                                                                          out, ldo, total, make_fastdiv(Cp / 4),
+                                                                          make_fastdiv(w), make_fastdiv(h));
     return mk_check_launch("mk_grid_sample_fwd");
 }
 
@@ -155,23 +131,23 @@ __global__ void __launch_bounds__(256) k_grid_sample_bwd(const float* __restrict
                                                          const float* __restrict__ deform, int d, int h0, int w0,
                                                          int mode, const float* __restrict__ dout, int ldo,
                                                          float* __restrict__ dinp, int lddi,
-                                                         float* __restrict__ ddeform, int seg, long long total_pad) {
+                                                         float* __restrict__ ddeform, int seg, long long total_pad,
+                                                         const FastDiv fcv, const FastDiv fw, const FastDiv fh) {
     // the host only enables the shuffle path (seg > 1) when total % 32 == 0, so warps are never partial there
-    const long long total = total_pad;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % cv) * 4;
-        const long long op = i / cv;
-        const int wo = (int)(op % w);
-        const long long t = op / w;
-        const int ho = (int)(t % h);
-        const long long n = t / h;
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= (unsigned)total_pad) return;
+    {
+        unsigned cq, wq, hq;
+        const unsigned op = fd_divmod(i, fcv, cq);
+        const unsigned t = fd_divmod(op, fw, wq);
+        const unsigned n = fd_divmod(t, fh, hq);
+        const int c = (int)cq * 4, wo = (int)wq, ho = (int)hq;
         const Tap tp = make_tap(fetch_grid(deform, n, h0, w0, ho, wo, h, w, mode), h, w);
-        const long long sb = (n / d) * (long long)h * w;
+        const long long sb = (long long)(n / (unsigned)d) * h * w;
         const bool xin0 = tp.x0 >= 0 && tp.x0 < w, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < w;
         const bool yin0 = tp.y0 >= 0 && tp.y0 < h, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < h;
         const float wx0 = 1.f - tp.wx1, wy0 = 1.f - tp.wy1;
-        const float4 g = ldg4(dout + op * ldo + c);
+        const float4 g = ldg4(dout + (long long)op * ldo + c);
         float gix = 0.f, giy = 0.f;
         const long long o00 = sb + (long long)tp.y0 * w + tp.x0, o01 = o00 + 1, o10 = o00 + w, o11 = o10 + 1;
         if (yin0 && xin0) {
@@ -204,7 +180,7 @@ __global__ void __launch_bounds__(256) k_grid_sample_bwd(const float* __restrict
                         giy += __shfl_xor_sync(0xffffffffu, giy, o);
                     }
                 }
-                if (((threadIdx.x & 31) & (seg - 1)) != 0) continue;
+                if (((threadIdx.x & 31) & (seg - 1)) != 0) return;
             }
             scatter_grid_grad(ddeform, n, h0, w0, ho, wo, h, w, mode, gix * 0.5f * (float)(w - 1),
                               giy * 0.5f * (float)(h - 1));
@@ -227,11 +203,10 @@ MK_EXPORT int mk_grid_sample_bwd(const float* inp, int B, int h, int w, int Cp, 
     if ((cv & (cv - 1)) == 0 && cv <= 32) seg = cv;
     else if (cv % 32 == 0) seg = 32;
     if (total % 32 != 0) seg = 1;
-    long long blocks = mk_cdiv(total, 256);
-    const long long cap = 32LL * mk_num_sms();
-    if (blocks > cap) blocks = cap;
-    k_grid_sample_bwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inp, h, w, cv, ld, deform, d, h0, w0, mode, dout,
-                                                                          ldo, dinp, lddi, ddeform, seg, total);
+    MK_REQUIRE(total < (1LL << 31), "mk_grid_sample_bwd: more than 2^31 work items");
+    k_grid_sample_bwd<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        inp, h, w, cv, ld, deform, d, h0, w0, mode, dout, ldo, dinp, lddi, ddeform, seg, total, make_fastdiv(cv),
+        make_fastdiv(w), make_fastdiv(h));
     return mk_check_launch("mk_grid_sample_bwd");
 }
 
@@ -290,7 +265,7 @@ __global__ void __launch_bounds__(256) k_resize_bwd(const float* __restrict__ do
         const int ho = (int)(t % h);
         const long long n = t / h;
         float* base = dx + n * (long long)h0 * w0 * ld + c;
-        const float4 g = ldg4(dout + op * ldo + c);
+        const float4 g = ldg4(dout + (long long)op * ldo + c);
         if (mode == 0) {
             int ys = nearest_src(ho, h0, h), xs = nearest_src(wo, w0, w);
             atomicAdd(reinterpret_cast<float4*>(base + ((long long)ys * w0 + xs) * ld), g);

@@ -100,16 +100,15 @@ MK_EXPORT int mk_nhwc_to_ncdhw(const float* src, int ld, int B, int C, int D, in
 // ------------------------------------------------------------------------------------------------ channel slices
 template <bool ADD>
 __global__ void k_copy_channels(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
-                                long long npix, int cv) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = npix * cv;
-    for (; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long p = i / cv;
-        int c = (int)(i % cv) * 4;
-        float4 v = ld4(src + p * lds + c);
-        if (ADD) v = v + ld4(dst + p * ldd + c);
-        st4(dst + p * ldd + c, v);
-    }
+                                long long total, const FastDiv fcv) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;  // one float4 per thread, 32-bit index math
+    if (i >= (unsigned)total) return;
+    unsigned cq;
+    const unsigned p = fd_divmod(i, fcv, cq);
+    const int c = (int)cq * 4;
+    float4 v = ld4(src + (long long)p * lds + c);
+    if (ADD) v = v + ld4(dst + (long long)p * ldd + c);
+    st4(dst + (long long)p * ldd + c, v);
 }
 
 static int copy_channels_impl(bool add, const float* src, int lds, float* dst, int ldd, long long npix, int C,
@@ -117,13 +116,12 @@ static int copy_channels_impl(bool add, const float* src, int lds, float* dst, i
     MK_REQUIRE(C % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "copy_channels: C/ld must be multiples of 4");
     long long total = npix * (C / 4);
     if (total == 0) return 0;
-    long long blocks = mk_cdiv(total, 256);
-    long long cap = (long long)mk_num_sms() * 16;
-    if (blocks > cap) blocks = cap;
+    MK_REQUIRE(total < (1LL << 31), "copy_channels: more than 2^31 work items");
+    const unsigned blocks = (unsigned)mk_cdiv(total, 256);
     if (add)
-        k_copy_channels<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, npix, C / 4);
+        k_copy_channels<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, total, make_fastdiv(C / 4));
     else
-        k_copy_channels<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, npix, C / 4);
+        k_copy_channels<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, total, make_fastdiv(C / 4));
     return mk_check_launch("copy_channels");
 }
 

@@ -19,7 +19,7 @@ using namespace mk_tc;
 
 constexpr int PC = 32;            // pixels per stage
 constexpr int BOX_BYTES = PC * 128;
-constexpr int WSTAGES = 4;
+constexpr int WSTAGES = 6;
 constexpr int WSTAGE_BYTES = 8 * BOX_BYTES;  // 4 A boxes + 4 B boxes
 constexpr int WSMEM_BYTES = WSTAGES * WSTAGE_BYTES + 1024 + 256;
 
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
     const int co0 = blockIdx.x * 128;
     const int tap = blockIdx.y / p.n_ci_tiles, ci0 = (blockIdx.y % p.n_ci_tiles) * 128;
     const int r = tap / p.S, s = tap - r * p.S;
-    const int n_this = min(128, p.Cin_p - ci0);          // multiple of 16 (host guarantees Cin_p % 16 == 0)
+    const int n_this = min(128, p.Cin_p - ci0);          // multiple of 4; the MMA runs on the next multiple of 16
     const int nb = (n_this + 31) >> 5;                   // B boxes actually needed
     const int q0 = blockIdx.z * p.chunks_per_split;
     const int q1 = min(p.nchunks, q0 + p.chunks_per_split);
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
         }
     } else if (warp == 1) {
         // M = 128 (co), N = n_this (ci), both operands MN-major
-        const uint32_t idesc = umma_idesc_tf32(128, n_this) | (1u << 15) | (1u << 16);
+        const uint32_t idesc = umma_idesc_tf32(128, (n_this + 15) & ~15) | (1u << 15) | (1u << 16);
         for (int it = 0; it < niter; ++it) {
             const int stage = it % WSTAGES;
             const uint32_t phase = (it / WSTAGES) & 1;
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
             if (!valid) continue;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
+                if (c + j >= n_this) break;  // ragged Cin_p: the extra columns are products with TMA zero fill
                 float* dst = base + (long long)(c + j) * p.Cout_p;
                 if (gridDim.z == 1) *dst = v[j];
                 else atomicAdd(dst, v[j]);
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
 
 MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,
                                  int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream) {
-    if (Cin_p % 16 || Cout_p % 16 || ldx % 4 || ldy % 4) {
+    if (Cin_p % 4 || Cout_p % 4 || ldx % 4 || ldy % 4) {
         mk_set_error("mk_conv2d_wgrad_tc: unsupported channel configuration");
         return -2;
     }

@@ -60,14 +60,25 @@ def set_conv_mode(mode):
     CONV_MODE = mode
 
 
-def _tc_ok(cin_p, cout_p, ups, pool, k=3, groups=1, for_dgrad=False):
-    """Envelope of mk_conv2d_tc.  The upsampled forward conv runs as four sub-pixel 2x2 convs (3x3 kernels only);
-    the input gradient of an upsampled conv keeps the FFMA kernel (its 2x2 sum-pool epilogue is the upsample transpose)."""
-    if CONV_MODE != 'tf32' or pool or cin_p < 8 or cout_p % 16 != 0:
+def _tc_ok(cin_p, cout_p, ups, pool, k=3, groups=1):
+    """Forward envelope of mk_conv2d_tc: everything but the fused-pool epilogue; the upsampled conv runs as four
+    sub-pixel 2x2 convs (3x3 ungrouped kernels)."""
+    if CONV_MODE != 'tf32' or pool:
         return False
-    if ups:
-        return (not for_dgrad) and k == 3 and groups == 1
-    return True
+    return (k == 3 and groups == 1) if ups else True
+
+
+_X4 = {}
+
+
+def _times4_params(cp, device):
+    """norm-apply parameter block [mean, invstd, scale, shift] with scale = 4: average-pool(4*x) == 2x2 sum."""
+    key = (cp, device)
+    if key not in _X4:
+        t = torch.zeros(4, cp, dtype=torch.float32, device=device)
+        t[2] = 4.0
+        _X4[key] = t.reshape(-1)
+    return _X4[key]
 
 
 def _channel_maps(segs, device):
@@ -236,15 +247,22 @@ class _Conv(torch.autograd.Function):
             dy = dz
         cmap, cinv = _channel_maps(segs, x.device)
         dx = dw = db = None
+        tc = CONV_MODE == 'tf32'
         if ctx.needs_input_grad[0]:
             wt = _empty(R * S * Cop * Cp, like=x)
-            tc = _tc_ok(Cop, Cp, ups, 0, R, groups, for_dgrad=True)
             lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop, 3 if tc else 1,
                      wt.data_ptr(), None, None, st)
             dx = _empty(N, Hin, Win, Cp, like=x)
-            # dgrad = correlation of dy with the flipped/transposed kernel, padding R-1-pad; the transpose of the
-            # nearest-x2 upsample is a 2x2 sum, fused as the conv's pooled epilogue
-            if tc:
+            # dgrad = correlation of dy with the flipped/transposed kernel, padding R-1-pad.  The transpose of the
+            # nearest-x2 upsample is a 2x2 sum: fused as the fp32 kernel's pooled epilogue; on the tensor-core path
+            # the full-resolution gradient is pooled by the (x4, average) mode of the norm-apply kernel.
+            if tc and ups:
+                full = _empty(N, dy.shape[1], dy.shape[2], Cp, like=x)
+                lib.call('mk_conv2d_tc', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
+                         R - 1 - pad, None, None, None, 0, 0, 0.0, full.data_ptr(), Cp, Cp, st)
+                lib.call('mk_norm_apply', full.data_ptr(), Cp, N, dy.shape[1], dy.shape[2], Cp,
+                         _times4_params(Cp, x.device).data_ptr(), 0, -1.0, 1, dx.data_ptr(), Cp, st)
+            elif tc:
                 lib.call('mk_conv2d_tc', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
                          R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, st)
             else:
@@ -252,9 +270,14 @@ class _Conv(torch.autograd.Function):
                          R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, 2 if ups else 0, st)
         if ctx.needs_input_grad[1]:
             dwp = _empty(R * S * Cp * Cop, like=x)
-            if CONV_MODE == 'tf32' and not ups and Cp % 16 == 0 and Cop % 16 == 0:
-                lib.call('mk_conv2d_wgrad_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, dy.data_ptr(), Cop, Cop, R, S, pad,
-                         dwp.data_ptr(), st)
+            if tc:
+                xin = x
+                if ups:  # the tensor-core wgrad reads the upsampled activation as a plain tensor (one resize kernel)
+                    xin = _empty(N, Hin * 2, Win * 2, Cp, like=x)
+                    lib.call('mk_resize_fwd', x.data_ptr(), N, Hin, Win, Cp, Cp, 0, xin.data_ptr(), Hin * 2, Win * 2, Cp,
+                             st)
+                lib.call('mk_conv2d_wgrad_tc', xin.data_ptr(), N, xin.shape[1], xin.shape[2], Cp, Cp, dy.data_ptr(), Cop,
+                         Cop, R, S, pad, dwp.data_ptr(), st)
             else:
                 lib.call('mk_conv2d_wgrad', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, dy.data_ptr(), Cop, Cop, R, S, pad,
                          dwp.data_ptr(), st)

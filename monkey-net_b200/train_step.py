@@ -118,7 +118,15 @@ class GraphedTrainer:
         for m, sd in zip(self.modules, snap[0]):
             m.load_state_dict(sd)
         for o, sd in zip(self.optimizers, snap[1]):
-            o.load_state_dict(sd)
+            if len(sd['state']) == 0:
+                # fresh optimiser: keep the (now allocated) moment / step tensors - the graph must capture only the
+                # update, not their lazy zero-initialisation - and reset their values in place
+                for st in o.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            else:
+                o.load_state_dict(sd)
 
     def _capture(self, x):
         self.static_in = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in x.items()}
