@@ -103,11 +103,15 @@ int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Cin_p, int l
  * bias gradients) or N (instance norm).  `sums` is [groups][2][Cp].  With several GPUs the [2][Cp] block is what
  * gets all-reduced (ONE NCCL all-reduce per BN layer per direction). */
 int mk_colstats(const float* x, int ld, int N, long long hw, int Cp, int per_frame, float* sums, void* stream);
-/* mean/invstd/scale/shift from (possibly all-reduced) sums.  count = pixels per group (global).  gamma/beta are
+/* the same sums accumulated and returned in DOUBLE precision (forward statistics of batch / instance norm: the
+ * variance E[x^2]-E[x]^2 cancels in fp32 when mean^2 >> var).  This [groups][2][Cp] double block is what the
+ * forward all-reduce carries. */
+int mk_colstats_f64(const float* x, int ld, int N, long long hw, int Cp, int per_frame, double* sums, void* stream);
+/* mean/invstd/scale/shift from (possibly all-reduced) double-precision sums of mk_colstats_f64.  count = pixels per group (global).  gamma/beta are
  * the logical-length-C parameters; padding channels get scale = shift = 0.  If running_mean != NULL the running
  * stats are updated (momentum, unbiased variance) and *num_batches_tracked (int64) is incremented.
  * out = [groups][4][Cp]: mean, invstd, scale, shift. */
-int mk_norm_finalize(const float* sums, int groups, int C, int Cp, double count, const float* gamma,
+int mk_norm_finalize(const double* sums, int groups, int C, int Cp, double count, const float* gamma,
                      const float* beta, float eps, float* running_mean, float* running_var, float momentum,
                      long long* num_batches_tracked, float* out, void* stream);
 /* eval-mode BN: scale/shift from running stats (batchnorm.py:50-53 with training=False); out as above, groups=1 */

@@ -87,6 +87,58 @@ __global__ void __launch_bounds__(256) k_colstats(const StatP p, int cv, int cvb
     }
 }
 
+// Forward statistics of a normalisation layer in DOUBLE precision: var = E[x^2] - E[x]^2 cancels catastrophically in
+// fp32 when mean^2 >> var (measured up to 90x on the dense-motion hourglass of shapes.yaml -> 1e-5 relative error of
+// the variance; ATen uses Welford for the same reason).  B200 runs FP64 at half the FP32 rate, and this kernel is
+// HBM-bound, so the double accumulators are free.  sums[g][2][Cp] doubles.
+struct D4 { double x, y, z, w; };
+__device__ __forceinline__ void d4acc(D4& a, float4 v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+__device__ __forceinline__ void d4acc2(D4& a, float4 v) {
+    a.x += (double)v.x * v.x; a.y += (double)v.y * v.y; a.z += (double)v.z * v.z; a.w += (double)v.w * v.w;
+}
+__device__ __forceinline__ void d4add(D4& a, const D4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+__global__ void __launch_bounds__(256) k_colstats_f64(const float* __restrict__ x, int ldx, long long pix_total,
+                                                      long long hw, int Cp, int per_frame, double* __restrict__ sums,
+                                                      int cv, int cvb, int rows) {
+    __shared__ D4 s0[256];
+    __shared__ D4 s1[256];
+    const int tid = threadIdx.x;
+    const int tv = tid % cvb, prow = tid / cvb;
+    const int vec = blockIdx.y * cvb + tv;
+    const int g = blockIdx.z;
+    const bool active = prow < rows && vec < cv;
+    D4 a0 = {0., 0., 0., 0.}, a1 = {0., 0., 0., 0.};
+    if (active) {
+        const int c = vec * 4;
+        const long long pix_base = per_frame ? (long long)g * hw : 0;
+        for (long long q = (long long)blockIdx.x * rows + prow; q < pix_total; q += (long long)gridDim.x * rows) {
+            const float4 v = ldg4(x + (pix_base + q) * ldx + c);
+            d4acc(a0, v);
+            d4acc2(a1, v);
+        }
+    }
+    s0[tid] = a0;
+    s1[tid] = a1;
+    __syncthreads();
+    int span = 1;
+    while (span < rows) span <<= 1;
+    for (int s = span >> 1; s > 0; s >>= 1) {
+        if (active && prow < s && prow + s < rows) {
+            d4add(s0[tid], s0[tid + s * cvb]);
+            d4add(s1[tid], s1[tid + s * cvb]);
+        }
+        __syncthreads();
+    }
+    if (active && prow == 0) {
+        double* o = sums + (long long)g * 2 * Cp + vec * 4;
+        const D4 r0 = s0[tid], r1 = s1[tid];
+        atomicAdd(o + 0, r0.x); atomicAdd(o + 1, r0.y); atomicAdd(o + 2, r0.z); atomicAdd(o + 3, r0.w);
+        o += Cp;
+        atomicAdd(o + 0, r1.x); atomicAdd(o + 1, r1.y); atomicAdd(o + 2, r1.z); atomicAdd(o + 3, r1.w);
+    }
+}
+
 template <int MODE>
 static int launch_colstats(StatP& p, cudaStream_t st, const char* what) {
     const int cv = p.Cp / 4;
@@ -116,6 +168,29 @@ MK_EXPORT int mk_colstats(const float* x, int ld, int N, long long hw, int Cp, i
     return launch_colstats<0>(p, (cudaStream_t)stream, "mk_colstats");
 }
 
+MK_EXPORT int mk_colstats_f64(const float* x, int ld, int N, long long hw, int Cp, int per_frame, double* sums,
+                              void* stream) {
+    MK_REQUIRE(Cp % 4 == 0 && ld % 4 == 0, "mk_colstats_f64: channels must be x4");
+    MK_REQUIRE(!per_frame || N <= 65535, "mk_colstats_f64: too many groups");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cv = Cp / 4;
+    const int cvb = cv < 64 ? cv : 64;
+    const int rows = 256 / cvb;
+    const int groups = per_frame ? N : 1;
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)Cp * groups, st);
+    if (e != cudaSuccess) { mk_set_error("mk_colstats_f64 memset: %s", cudaGetErrorString(e)); return (int)e; }
+    const long long pix = per_frame ? hw : (long long)N * hw;
+    if (pix == 0) return 0;
+    const int ychunks = (int)mk_cdiv(cv, cvb);
+    long long nblk = mk_cdiv(pix, (long long)rows * 8);
+    long long cap = mk_cdiv(4LL * mk_num_sms(), (long long)ychunks * groups);
+    if (nblk > cap) nblk = cap;
+    if (nblk < 1) nblk = 1;
+    dim3 grid((unsigned)nblk, (unsigned)ychunks, (unsigned)groups);
+    k_colstats_f64<<<grid, 256, 0, st>>>(x, ld, pix, hw, Cp, per_frame, sums, cv, cvb, rows);
+    return mk_check_launch("mk_colstats_f64");
+}
+
 MK_EXPORT int mk_norm_bwd_reduce(const float* x, int ldx, const float* dout, int ldd, int N, int H, int W, int Cp,
                                  const float* params, int per_frame, float slope, int pool, float* sums,
                                  void* stream) {
@@ -129,7 +204,7 @@ MK_EXPORT int mk_norm_bwd_reduce(const float* x, int ldx, const float* dout, int
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
-__global__ void k_norm_finalize(const float* __restrict__ sums, int groups, int C, int Cp, double count,
+__global__ void k_norm_finalize(const double* __restrict__ sums, int groups, int C, int Cp, double count,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                 float* running_mean, float* running_var, float momentum, long long* nbt,
                                 float* __restrict__ out) {
@@ -160,7 +235,7 @@ __global__ void k_norm_finalize(const float* __restrict__ sums, int groups, int 
     }
 }
 
-MK_EXPORT int mk_norm_finalize(const float* sums, int groups, int C, int Cp, double count, const float* gamma,
+MK_EXPORT int mk_norm_finalize(const double* sums, int groups, int C, int Cp, double count, const float* gamma,
                                const float* beta, float eps, float* running_mean, float* running_var,
                                float momentum, long long* num_batches_tracked, float* out, void* stream) {
     int total = groups * Cp;
