@@ -43,6 +43,10 @@ def parse():
     ap.add_argument('--cpu-batch', type=int, default=None, help='batch of the CPU baseline sample')
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'],
                     help='run the iteration as one CUDA graph launch (monkey_net_b200.train_step.GraphedTrainer)')
+    ap.add_argument('--workload', default='train', choices=['train', 'transfer'],
+                    help="train = configs[1] (the headline); transfer = configs[2]: moving-gif nets, 256x256, "
+                         "transfer_one on 16 sources x 2 driving frames (use --config moving-gif --res 256 --batch 16)")
+    ap.add_argument('--no-transfer', action='store_true', help='skip the 256x256 transfer side measurement')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-bench', action='store_true')
     return ap.parse_args()
@@ -280,9 +284,111 @@ def run_ours(args):
         out['kernels'] = kernel_bench(device, pk)
     if not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(args, cfg)
+    if world == 1 and not args.no_transfer:
+        del trainer, gen, disc, kp
+        torch.cuda.empty_cache()
+        out['transfer_256'] = transfer_bench(device, 'moving-gif', 256, 16, 2, args.steps, args.warmup,
+                                             cpu=not args.no_cpu_baseline)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def transfer_bench(device, config, res, batch, d, steps, warmup, cpu=True):
+    """BASELINE.json configs[2] / north-star 256x256 transfer: `config` nets at res x res, eval mode, transfer_one
+    (transfer.py:65-79) on `batch` sources x `d` driving frames = batch*d generated frames per call.  `value`: inputs
+    resident in HBM; `e2e`: pinned host inputs -> H2D -> graph -> D2H of the predicted frames (what transfer.py:116
+    does with `.data.cpu().numpy()`); `cpu_baseline`: the oracle's transfer_one on a bounded sample."""
+    from monkey_net_b200 import lib, transfer_step
+    from monkey_net_b200 import ops as mkops
+    cfg = load_config(config)
+    gen, disc, kp = build_nets(cfg, device)
+    del disc
+    x = {'source': torch.rand(batch, 3, 1, res, res), 'driving': torch.rand(batch, 3, d, res, res)}
+    with torch.no_grad():  # populate the BN running statistics the way a trained checkpoint would carry them
+        for m in (gen, kp):
+            m.train()
+        kj = kp(torch.cat([x['source'][:2], x['driving'][:2, :, :1]], 2).to(device))
+        gen(x['source'][:2].to(device), {k: v[:, 1:] for k, v in kj.items()}, {k: v[:, :1] for k, v in kj.items()})
+    for m in (gen, kp):
+        m.eval()
+    tparams = cfg['transfer_params']
+    runner = transfer_step.GraphedTransfer(gen, kp, tparams, use_graph=True)
+    host = {k: v.pin_memory() for k, v in x.items()}
+    resident = {k: v.to(device) for k, v in x.items()}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    out_host = torch.empty(batch, 3, d, res, res).pin_memory()
+
+    def timed(fn, n):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        torch.cuda.synchronize()
+        for s_, e_ in evs:
+            lib.call('mk_fill_zero', flush.data_ptr(), flush.numel(), torch.cuda.current_stream().cuda_stream)
+            s_.record(); fn(); e_.record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / n
+
+    def call_resident():
+        runner.run(resident['source'], resident['driving'])
+
+    def call_e2e():
+        o = runner.run(host['source'], host['driving'])
+        out_host.copy_(o['video_prediction'], non_blocking=True)
+
+    for _ in range(max(2, warmup)):
+        call_resident()
+    ms = timed(call_resident, steps)
+    call_e2e()
+    ms_e2e = timed(call_e2e, steps)
+    frames = batch * d
+    r = {'workload': 'config/%s.yaml nets @%dx%d, eval, transfer_one: %d sources x %d driving frames per call, CUDA '
+                     'graph, all driving frames batched into one KP + one generator pass' % (config, res, res, batch, d),
+         'metric': 'generated frames/sec (transfer)', 'value': frames / (ms / 1e3), 'unit': 'frames/s',
+         'ms_per_call': ms, 'conv_mode': mkops.CONV_MODE, 'kernels_per_call': runner.kernels_per_call,
+         'e2e': {'value': frames / (ms_e2e / 1e3), 'unit': 'frames/s',
+                 'h2d_bytes_per_step': sum(v.numel() * 4 for v in host.values()),
+                 'd2h_bytes_per_step': out_host.numel() * 4}}
+    if cpu:
+        r['cpu_baseline'] = cpu_transfer_baseline(cfg, config, res, 2, d)
+        r['e2e_speedup_vs_cpu'] = r['e2e']['value'] / r['cpu_baseline']['value']
+    del runner, gen, kp
+    torch.cuda.empty_cache()
+    return r
+
+
+def cpu_transfer_baseline(cfg, config, res, batch, d):
+    from oracle import monkey_oracle as mo
+    og, od, ok = mo.build_from_config(cfg)
+    torch.manual_seed(0)
+    for m in (og, ok):
+        m.eval()
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
+    x = {'source': torch.rand(batch, 3, 1, res, res), 'driving': torch.rand(batch, 3, d, res, res)}
+    norm = cfg['transfer_params']['normalization_params']
+    best = None
+    probe = {}
+    for c in sorted({c for c in (16, 32, 64, ncpu) if c <= ncpu}):
+        torch.set_num_threads(c)
+        with torch.no_grad():
+            mo.transfer_one(og, ok, x['source'], x['driving'], norm)  # warm-up (oneDNN primitive creation)
+            t0 = time.perf_counter()
+            mo.transfer_one(og, ok, x['source'], x['driving'], norm)
+            t = time.perf_counter() - t0
+        probe[c] = round(batch * d / t, 2)
+        if best is None or t < best[1]:
+            best = (c, t)
+    torch.set_num_threads(best[0])
+    ts = []
+    with torch.no_grad():
+        for _ in range(3):
+            t0 = time.perf_counter()
+            mo.transfer_one(og, ok, x['source'], x['driving'], norm)
+            ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return {'value': batch * d / ts[1], 'unit': 'frames/s', 'cores': best[0], 'kind': 'port',
+            'sample': 'oracle transfer_one (per-frame loop of transfer.py:65-79), %s.yaml @%dx%d, %d sources x %d '
+                      'driving frames, median of 3 after warm-up; %d of %d host threads (fastest of %s)'
+                      % (config, res, res, batch, d, best[0], ncpu, probe)}
 
 
 def kernel_bench(device, pk):
@@ -406,9 +512,63 @@ def run_reference(args):
         'e2e': {'value': val, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
+def run_transfer(args):
+    """--workload transfer: the 256x256 transfer configuration as the bench line itself (replicas only for N > 1:
+    eval-mode inference has no exchange step)."""
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    cfgname = args.config if args.config != 'shapes' else 'moving-gif'
+    res = args.res if args.res != 64 else 256
+    batch = args.batch if args.batch != 32 else 16
+    if args.impl == 'reference':
+        if rank == 0:
+            cb = cpu_transfer_baseline(load_config(cfgname), cfgname, res, 2, 2)
+            print(json.dumps({'impl': 'reference', 'metric': 'generated frames/sec (transfer)', 'value': cb['value'],
+                              'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': 3, 'warmup': 1,
+                              'ms_per_step': 4 / cb['value'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+                              'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                              'config': {'workload': cb['sample']}, 'cpu_baseline': cb,
+                              'e2e': {'value': cb['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0,
+                                      'd2h_bytes_per_step': 0}}))
+        return
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    r = transfer_bench(device, cfgname, res, batch, 2, args.steps, args.warmup,
+                       cpu=(rank == 0 and not args.no_cpu_baseline))
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([r['ms_per_call'], 1e3 * batch * 2 / r['e2e']['value']], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        frames = batch * 2 * world
+        out = {'metric': r['metric'], 'value': frames / (float(t[0]) / 1e3), 'unit': 'frames/s', 'n_gpus': world,
+               'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(t[0]), 'higher_is_better': True,
+               'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'tf32 tensor-core convs (fp32 accumulate), fp32 elsewhere' if r['conv_mode'] == 'tf32' else 'f32',
+               'data': 'synthetic (torch.rand frames, seeded default-init weights)',
+               'config': {'workload': r['workload'], 'parallelism': 'replicas x%d' % world,
+                          'l2': 'flushed between timed calls'},
+               'e2e': dict(r['e2e'], value=frames / (float(t[1]) / 1e3)),
+               'gpu_launches': r['kernels_per_call'] * args.steps, 'clocks': clocks}
+        if 'cpu_baseline' in r:
+            out['cpu_baseline'] = r['cpu_baseline']
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == '__main__':
     a = parse()
-    if a.impl == 'reference':
+    if a.workload == 'transfer':
+        run_transfer(a)
+    elif a.impl == 'reference':
         run_reference(a)
     else:
         run_ours(a)

@@ -12,7 +12,13 @@
 //   activation -> 128-bit stores).  smem ring of STAGES stages with full/empty mbarriers; accumulator handed over
 //   through a tmem_full mbarrier.  The ring takes ~200 KB (6-8 stages): at these sizes the K loop is bound by the
 //   TMA round trip, not by the MMA issue rate, so depth beats a second resident CTA.
-// Same contract as mk_conv2d (conv.cu) for stride-1 convs without the upsample / pool options.
+// * Occupancy instead of one fat CTA per SM: the ring is sized to the K loop actually run (2-8 stages) inside a
+//   budget that lets 2-3 CTAs share an SM (TMEM columns are allocated to the tile's N, 32..128), so one CTA's
+//   prologue / epilogue overlaps its neighbours' main loops.
+// * split-K (grid.z): layers whose tile count cannot fill 148 SMs (deep, low-resolution levels: 128 pixels x 1152 K)
+//   split the (tap, channel-chunk) loop over several CTAs that combine with red.global.add.v4.f32 into the
+//   zero-initialised output; split 0 carries the bias / residual.  Only for the linear epilogue (act == 0).
+// Same contract as mk_conv2d (conv.cu) for stride-1 convs without the pool option.
 #include "common.cuh"
 #include "../../include/monkey_b200.h"
 #include "tc_common.cuh"
@@ -26,7 +32,6 @@ constexpr int KC = 32;         // fp32 channels per stage = 128 bytes = one swiz
 constexpr int MAX_STAGES = 8;   // the ring is as deep as ~200 KB of shared memory allows: the K loop of these convs is
                                 // TMA-latency bound (~1 us round trip vs ~0.13 us of MMA per stage), not MMA bound
 constexpr int A_BYTES = BM * KC * 4;
-constexpr int SMEM_BUDGET = 200 * 1024;
 constexpr int SMEM_MAX = 227 * 1024;
 
 struct TcP {
@@ -34,6 +39,7 @@ struct TcP {
     int ups;  // 1: nearest-x2-upsampled 3x3 conv as four 2x2 sub-pixel convs (grid.z = output parity)
     int TW, TH, TN, tilesW, tilesH;
     int nstages, stage_bytes;  // smem ring: stage = A tile (16 KB) + B tile (b_rows x 128 B)
+    int ksplit, iters_per_split, tmem_cols;
     const float* scale; const float* shift; const float* resid; int ldr, act; float slope;
     float* y;
 };
@@ -57,12 +63,15 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     const int cout0 = blockIdx.y * BN_MAX;
     const int n_this = min(BN_MAX, p.Cout_p - cout0);
     const int nchunks = (p.Cin_p + KC - 1) / KC;
-    const int niter = p.R * p.S * nchunks;
+    const int split = (int)blockIdx.z % p.ksplit, zpar = (int)blockIdx.z / p.ksplit;
+    const int it0 = split * p.iters_per_split;
+    const int it1 = min(p.R * p.S * nchunks, it0 + p.iters_per_split);
+    const int niter = it1 - it0;  // >= 1 by construction of ksplit
     // sub-pixel decomposition of conv3x3(upsample2x(x)): output parity (py,px) is a 2x2 conv of x whose taps are
     // sums of the 3x3 taps (pre-summed by mk_pack_weight mode 4) with row offsets {-1,0} (py=0) or {0,+1} (py=1)
-    const int py = p.ups ? (int)(blockIdx.z >> 1) : 0, px = p.ups ? (int)(blockIdx.z & 1) : 0;
+    const int py = p.ups ? (zpar >> 1) : 0, px = p.ups ? (zpar & 1) : 0;
     const int pad_h = p.ups ? 1 - py : p.pad, pad_w = p.ups ? 1 - px : p.pad;
-    const int tap0 = p.ups ? (int)blockIdx.z * 4 : 0;
+    const int tap0 = p.ups ? zpar * 4 : 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -75,7 +84,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)BN_MAX)
+                     "r"((uint32_t)p.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -87,9 +96,10 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (elect_one()) {
-            for (int it = 0; it < niter; ++it) {
-                const int stage = it % STAGES;
-                const uint32_t phase = (it / STAGES) & 1;
+            for (int li = 0; li < niter; ++li) {
+                const int stage = li % STAGES;
+                const uint32_t phase = (li / STAGES) & 1;
+                const int it = it0 + li;
                 const int tap = it / nchunks, ch = it - tap * nchunks;
                 const int r = tap / p.S, s = tap - r * p.S;
                 mbar_wait(&empty[stage], phase ^ 1);
@@ -102,10 +112,10 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
         const uint32_t idesc = umma_idesc_tf32(BM, (n_this + 15) & ~15);  // rows beyond Cout_p are TMA zero fill
-        for (int it = 0; it < niter; ++it) {
-            const int stage = it % STAGES;
-            const uint32_t phase = (it / STAGES) & 1;
-            const int ch = it % nchunks;
+        for (int li = 0; li < niter; ++li) {
+            const int stage = li % STAGES;
+            const uint32_t phase = (li / STAGES) & 1;
+            const int ch = (it0 + li) % nchunks;
             mbar_wait(&full[stage], phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
@@ -115,9 +125,9 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                 if (kleft > KC) kleft = KC;
                 const int nk = (kleft + 7) >> 3;  // UMMA K = 8 tf32 (32 bytes); the TMA zero-fills the ragged tail
                 for (int k = 0; k < nk; ++k)      // advancing 32 B inside the 128 B swizzle row = +2 in 16 B units
-                    umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) ? 1u : 0u);
+                    umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (li | k) ? 1u : 0u);
                 umma_commit(&empty[stage]);       // frees the smem stage when these MMAs retire
-                if (it == niter - 1) umma_commit(tmem_full);
+                if (li == niter - 1) umma_commit(tmem_full);
             }
             __syncwarp();
         }
@@ -143,6 +153,15 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             for (int j = 0; j < 16; j += 4) {
                 if (c + j >= n_this) break;  // ragged Cout_p (multiple of 4, not of 16)
                 float4 sc = p.scale ? ldg4(p.scale + co + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+                if (p.ksplit > 1) {  // partial sum of a split-K tile: linear epilogue, split 0 adds bias + residual
+                    float4 o = make_float4(v[j] * sc.x, v[j + 1] * sc.y, v[j + 2] * sc.z, v[j + 3] * sc.w);
+                    if (split == 0) {
+                        if (p.shift) o = o + ldg4(p.shift + co + j);
+                        if (p.resid) o = o + ldg4(p.resid + pix * p.ldr + co + j);
+                    }
+                    atomicAdd(reinterpret_cast<float4*>(p.y + pix * p.ldy + co + j), o);
+                    continue;
+                }
                 float4 sh = p.shift ? ldg4(p.shift + co + j) : f4zero();
                 float4 o = make_float4(fmaf(v[j], sc.x, sh.x), fmaf(v[j + 1], sc.y, sh.y), fmaf(v[j + 2], sc.z, sh.z),
                                        fmaf(v[j + 3], sc.w, sh.w));
@@ -161,7 +180,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN_MAX)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                      : "memory");
     }
 }
@@ -199,7 +218,30 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
 
     const int b_rows = Cout_p < BN_MAX ? (Cout_p + 15) & ~15 : BN_MAX;  // weight rows per stage = UMMA N
     p.stage_bytes = A_BYTES + b_rows * KC * 4;
-    p.nstages = SMEM_BUDGET / p.stage_bytes < MAX_STAGES ? SMEM_BUDGET / p.stage_bytes : MAX_STAGES;
+    p.tmem_cols = b_rows <= 32 ? 32 : (b_rows <= 64 ? 64 : 128);
+    const int grid_y = (Cout_p + BN_MAX - 1) / BN_MAX;
+    const long long tiles = (long long)p.tilesW * p.tilesH * tilesN * grid_y * (p.ups ? 4 : 1);
+    const int niter_total = R * S * ((Cin_p + KC - 1) / KC);
+    const int sms = mk_num_sms();
+    // split-K only for the linear epilogue into a dense output, when the tiles alone leave most SMs idle
+    p.ksplit = 1;
+    if (act == 0 && ldy == Cout_p && tiles * 2 <= sms && niter_total >= 4) {
+        long long want = (2LL * sms + tiles - 1) / tiles;
+        if (want > niter_total / 2) want = niter_total / 2;  // at least 2 K iterations per CTA
+        if (want > 64) want = 64;
+        if (want > 1) p.ksplit = (int)want;
+    }
+    p.iters_per_split = (niter_total + p.ksplit - 1) / p.ksplit;
+    p.ksplit = (niter_total + p.iters_per_split - 1) / p.iters_per_split;
+    // ring depth: never deeper than the K loop; shallow enough for 2-3 resident CTAs when there are CTAs to overlap
+    const long long ctas = tiles * p.ksplit;
+    const int budget = ctas > 2LL * sms ? (p.stage_bytes <= 24 * 1024 ? 72 * 1024 : 108 * 1024)
+                                        : (ctas > sms ? 108 * 1024 : 200 * 1024);
+    int nst = budget / p.stage_bytes;
+    if (nst > MAX_STAGES) nst = MAX_STAGES;
+    if (nst > p.iters_per_split) nst = p.iters_per_split;
+    if (nst < 2) nst = 2;
+    p.nstages = nst;
     const int smem_bytes = p.nstages * p.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
     CUtensorMap tmA, tmB;
     {
@@ -228,7 +270,12 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
         if (e != cudaSuccess) { mk_set_error("mk_conv2d_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
-    dim3 grid((unsigned)(p.tilesW * p.tilesH * tilesN), (unsigned)((Cout_p + BN_MAX - 1) / BN_MAX), p.ups ? 4 : 1);
+    if (p.ksplit > 1) {
+        const size_t out_pix = (size_t)N * p.Ho * p.Wo * (p.ups ? 4 : 1);
+        cudaError_t e = cudaMemsetAsync(y, 0, out_pix * ldy * sizeof(float), (cudaStream_t)stream);
+        if (e != cudaSuccess) { mk_set_error("mk_conv2d_tc memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    dim3 grid((unsigned)(p.tilesW * p.tilesH * tilesN), (unsigned)grid_y, (unsigned)((p.ups ? 4 : 1) * p.ksplit));
     k_conv_tc<<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
     return mk_check_launch("mk_conv2d_tc");
 }

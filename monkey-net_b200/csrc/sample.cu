@@ -52,35 +52,59 @@ __device__ __forceinline__ Tap make_tap(float2 g, int h, int w) {
     return t;
 }
 
+// Work decomposition (forward and backward): one CTA owns a PH x PW patch of output pixels of one frame and all of its
+// channel vectors; item = (pixel of the patch, float4 of channels), channel vector fastest, so the lanes of a warp
+// are the channels of 1-2 neighbouring pixels (128-bit loads that coalesce into whole 128 B lines per tap).  The
+// four taps of neighbouring pixels overlap (x0+1 of pixel w is x0 of pixel w+1, row y0+1 of this row is row y0 of the
+// next): with the previous row-linear mapping every tap line was fetched again from L2 by another CTA (ncu: L1 hit
+// 21 %, L2->SM traffic 4x the input, the kernel ran at the L2 bandwidth, 48 % of HBM); a 2-D patch keeps that reuse
+// inside one SM's L1.
+struct Patch {
+    int ph, pw, pw_sh, tiles_x, tiles_y, items;  // pw = 1 << pw_sh; items = ph * pw * cv
+};
+
+static inline Patch make_patch(int h, int w, int cv) {
+    Patch t;
+    const int side = cv >= 16 ? 8 : 16;
+    t.ph = side; t.pw = side; t.pw_sh = side == 8 ? 3 : 4;
+    t.tiles_x = (w + t.pw - 1) / t.pw; t.tiles_y = (h + t.ph - 1) / t.ph;
+    t.items = t.ph * t.pw * cv;
+    return t;
+}
+
 __global__ void __launch_bounds__(256) k_grid_sample_fwd(const float* __restrict__ inp, int h, int w, int cv, int ld,
                                                          const float* __restrict__ deform, int d, int h0, int w0,
-                                                         int mode, float* __restrict__ out, int ldo, long long total,
-                                                         const FastDiv fcv, const FastDiv fw, const FastDiv fh) {
-    // one item (pixel, float4 of channels) per thread, 32-bit index math (see FastDiv): occupancy, not per-thread
-    // unrolling, supplies the memory-level parallelism here - a 4-item unroll measured 13 % slower (profiles/r1)
-    const unsigned i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= (unsigned)total) return;
-    unsigned cq, wo, ho;
-    const unsigned op = fd_divmod(i, fcv, cq);
-    const unsigned t = fd_divmod(op, fw, wo);
-    const unsigned n = fd_divmod(t, fh, ho);
-    const int c = (int)cq * 4;
-    const Tap tp = make_tap(fetch_grid(deform, n, h0, w0, (int)ho, (int)wo, h, w, mode), h, w);
-    const float* src = inp + (long long)(n / (unsigned)d) * h * w * ld + c;
-    const bool xin0 = tp.x0 >= 0 && tp.x0 < w, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < w;
-    const bool yin0 = tp.y0 >= 0 && tp.y0 < h, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < h;
-    const float wx0 = 1.f - tp.wx1, wy0 = 1.f - tp.wy1;
-    // issue the four tap loads before blending (ATen order: nw, ne, sw, se)
-    const float4 v0 = (yin0 && xin0) ? ldg4(src + (tp.y0 * w + tp.x0) * (long long)ld) : f4zero();
-    const float4 v1 = (yin0 && xin1) ? ldg4(src + (tp.y0 * w + tp.x0 + 1) * (long long)ld) : f4zero();
-    const float4 v2 = (yin1 && xin0) ? ldg4(src + ((tp.y0 + 1) * w + tp.x0) * (long long)ld) : f4zero();
-    const float4 v3 = (yin1 && xin1) ? ldg4(src + ((tp.y0 + 1) * w + tp.x0 + 1) * (long long)ld) : f4zero();
-    float4 acc = f4zero();
-    fma4(acc, v0, wx0 * wy0);
-    fma4(acc, v1, tp.wx1 * wy0);
-    fma4(acc, v2, wx0 * tp.wy1);
-    fma4(acc, v3, tp.wx1 * tp.wy1);
-    st4(out + (long long)op * ldo + c, acc);
+                                                         int mode, float* __restrict__ out, int ldo, const Patch pt,
+                                                         const FastDiv fcv, const FastDiv ftx, const FastDiv fty) {
+    unsigned tx, ty;
+    const unsigned t1 = fd_divmod(blockIdx.x, ftx, tx);
+    const unsigned n = fd_divmod(t1, fty, ty);
+    const float* src = inp + (long long)(n / (unsigned)d) * h * w * ld;
+    float* dst = out + (long long)n * h * w * ldo;
+#pragma unroll 2
+    for (unsigned item = threadIdx.x; item < (unsigned)pt.items; item += 256u) {
+        unsigned cq;
+        const unsigned p = fd_divmod(item, fcv, cq);
+        const int ho = (int)(ty * pt.ph + (p >> pt.pw_sh)), wo = (int)(tx * pt.pw + (p & (pt.pw - 1)));
+        if (ho >= h || wo >= w) continue;
+        const int c = (int)cq * 4;
+        const Tap tp = make_tap(fetch_grid(deform, n, h0, w0, ho, wo, h, w, mode), h, w);
+        const bool xin0 = tp.x0 >= 0 && tp.x0 < w, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < w;
+        const bool yin0 = tp.y0 >= 0 && tp.y0 < h, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < h;
+        const float wx0 = 1.f - tp.wx1, wy0 = 1.f - tp.wy1;
+        const float* s0 = src + (tp.y0 * w + tp.x0) * (long long)ld + c;
+        // issue the four tap loads before blending (ATen order: nw, ne, sw, se)
+        const float4 v0 = (yin0 && xin0) ? ldg4(s0) : f4zero();
+        const float4 v1 = (yin0 && xin1) ? ldg4(s0 + ld) : f4zero();
+        const float4 v2 = (yin1 && xin0) ? ldg4(s0 + (long long)w * ld) : f4zero();
+        const float4 v3 = (yin1 && xin1) ? ldg4(s0 + (long long)w * ld + ld) : f4zero();
+        float4 acc = f4zero();
+        fma4(acc, v0, wx0 * wy0);
+        fma4(acc, v1, tp.wx1 * wy0);
+        fma4(acc, v2, wx0 * tp.wy1);
+        fma4(acc, v3, tp.wx1 * tp.wy1);
+        __stcs(reinterpret_cast<float4*>(dst + ((long long)ho * w + wo) * ldo + c), acc);  // streamed: never re-read here
+    }
 }
 
 MK_EXPORT int mk_grid_sample_fwd(const float* inp, int B, int h, int w, int Cp, int ld, const float* deform, int d,
@@ -88,11 +112,13 @@ MK_EXPORT int mk_grid_sample_fwd(const float* inp, int B, int h, int w, int Cp, 
     MK_REQUIRE(Cp % 4 == 0 && ld % 4 == 0 && ldo % 4 == 0, "mk_grid_sample_fwd: channels must be x4");
     const long long total = (long long)B * d * h * w * (Cp / 4);
     if (total == 0) return 0;
-    MK_REQUIRE(total < (1LL << 31), "mk_grid_sample_fwd: more than 2^31 work items");
-    const long long blocks = mk_cdiv(total, 256);
+    const Patch pt = make_patch(h, w, Cp / 4);
+    const long long blocks = (long long)B * d * pt.tiles_x * pt.tiles_y;
+    MK_REQUIRE(blocks < (1LL << 31) && (long long)h * w * ld < (1LL << 31), "mk_grid_sample_fwd: extent too large");
     k_grid_sample_fwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(inp, h, w, Cp / 4, ld, deform, d, h0, w0, mode,
-                                                                          out, ldo, total, make_fastdiv(Cp / 4),
-                                                                          make_fastdiv(w), make_fastdiv(h));
+                                                                          out, ldo, pt, make_fastdiv(Cp / 4),
+                                                                          make_fastdiv(pt.tiles_x),
+                                                                          make_fastdiv(pt.tiles_y));
     return mk_check_launch("mk_grid_sample_fwd");
 }
 
@@ -131,44 +157,49 @@ __global__ void __launch_bounds__(256) k_grid_sample_bwd(const float* __restrict
                                                          const float* __restrict__ deform, int d, int h0, int w0,
                                                          int mode, const float* __restrict__ dout, int ldo,
                                                          float* __restrict__ dinp, int lddi,
-                                                         float* __restrict__ ddeform, int seg, long long total_pad,
-                                                         const FastDiv fcv, const FastDiv fw, const FastDiv fh) {
-    // the host only enables the shuffle path (seg > 1) when total % 32 == 0, so warps are never partial there
-    const unsigned i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= (unsigned)total_pad) return;
-    {
-        unsigned cq, wq, hq;
-        const unsigned op = fd_divmod(i, fcv, cq);
-        const unsigned t = fd_divmod(op, fw, wq);
-        const unsigned n = fd_divmod(t, fh, hq);
-        const int c = (int)cq * 4, wo = (int)wq, ho = (int)hq;
-        const Tap tp = make_tap(fetch_grid(deform, n, h0, w0, ho, wo, h, w, mode), h, w);
-        const long long sb = (long long)(n / (unsigned)d) * h * w;
-        const bool xin0 = tp.x0 >= 0 && tp.x0 < w, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < w;
-        const bool yin0 = tp.y0 >= 0 && tp.y0 < h, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < h;
-        const float wx0 = 1.f - tp.wx1, wy0 = 1.f - tp.wy1;
-        const float4 g = ldg4(dout + (long long)op * ldo + c);
+                                                         float* __restrict__ ddeform, int seg, const Patch pt,
+                                                         const FastDiv fcv, const FastDiv ftx, const FastDiv fty) {
+    // same patch decomposition as the forward kernel.  pt.items is a multiple of 32 and the item loop advances whole
+    // warps, so the lanes of one pixel (cv consecutive items) never straddle a loop boundary; pixels outside the
+    // image (partial patches) take part in the shuffles with zero contributions.
+    unsigned tx, ty;
+    const unsigned t1 = fd_divmod(blockIdx.x, ftx, tx);
+    const unsigned n = fd_divmod(t1, fty, ty);
+    const long long sb = (long long)(n / (unsigned)d) * h * w;
+    for (unsigned item = threadIdx.x; item < (unsigned)pt.items; item += 256u) {
+        unsigned cq;
+        const unsigned p = fd_divmod(item, fcv, cq);
+        const int ho = (int)(ty * pt.ph + (p >> pt.pw_sh)), wo = (int)(tx * pt.pw + (p & (pt.pw - 1)));
+        const bool inside = ho < h && wo < w;
+        const int c = (int)cq * 4;
         float gix = 0.f, giy = 0.f;
-        const long long o00 = sb + (long long)tp.y0 * w + tp.x0, o01 = o00 + 1, o10 = o00 + w, o11 = o10 + 1;
-        if (yin0 && xin0) {
-            if (dinp) atomicAdd(reinterpret_cast<float4*>(dinp + o00 * lddi + c), g * (wx0 * wy0));
-            float s = dot4(ldg4(inp + o00 * ld + c), g);
-            gix -= s * wy0; giy -= s * wx0;
-        }
-        if (yin0 && xin1) {
-            if (dinp) atomicAdd(reinterpret_cast<float4*>(dinp + o01 * lddi + c), g * (tp.wx1 * wy0));
-            float s = dot4(ldg4(inp + o01 * ld + c), g);
-            gix += s * wy0; giy -= s * tp.wx1;
-        }
-        if (yin1 && xin0) {
-            if (dinp) atomicAdd(reinterpret_cast<float4*>(dinp + o10 * lddi + c), g * (wx0 * tp.wy1));
-            float s = dot4(ldg4(inp + o10 * ld + c), g);
-            gix -= s * tp.wy1; giy += s * wx0;
-        }
-        if (yin1 && xin1) {
-            if (dinp) atomicAdd(reinterpret_cast<float4*>(dinp + o11 * lddi + c), g * (tp.wx1 * tp.wy1));
-            float s = dot4(ldg4(inp + o11 * ld + c), g);
-            gix += s * tp.wy1; giy += s * tp.wx1;
+        if (inside) {
+            const Tap tp = make_tap(fetch_grid(deform, n, h0, w0, ho, wo, h, w, mode), h, w);
+            const bool xin0 = tp.x0 >= 0 && tp.x0 < w, xin1 = tp.x0 + 1 >= 0 && tp.x0 + 1 < w;
+            const bool yin0 = tp.y0 >= 0 && tp.y0 < h, yin1 = tp.y0 + 1 >= 0 && tp.y0 + 1 < h;
+            const float wx0 = 1.f - tp.wx1, wy0 = 1.f - tp.wy1;
+            const float4 g = ldg4(dout + ((long long)n * h * w + (long long)ho * w + wo) * ldo + c);
+            const long long o00 = sb + (long long)tp.y0 * w + tp.x0, o01 = o00 + 1, o10 = o00 + w, o11 = o10 + 1;
+            if (yin0 && xin0) {
+                if (dinp) atomicAdd(reinterpret_cast<float4*>(dinp + o00 * lddi + c), g * (wx0 * wy0));
+                float s = dot4(ldg4(inp + o00 * ld + c), g);
+                gix -= s * wy0; giy -= s * wx0;
+            }
+            if (yin0 && xin1) {
+                if (dinp) atomicAdd(reinterpret_cast<float4*>(dinp + o01 * lddi + c), g * (tp.wx1 * wy0));
+                float s = dot4(ldg4(inp + o01 * ld + c), g);
+                gix += s * wy0; giy -= s * tp.wx1;
+            }
+            if (yin1 && xin0) {
+                if (dinp) atomicAdd(reinterpret_cast<float4*>(dinp + o10 * lddi + c), g * (wx0 * tp.wy1));
+                float s = dot4(ldg4(inp + o10 * ld + c), g);
+                gix -= s * tp.wy1; giy += s * wx0;
+            }
+            if (yin1 && xin1) {
+                if (dinp) atomicAdd(reinterpret_cast<float4*>(dinp + o11 * lddi + c), g * (tp.wx1 * tp.wy1));
+                float s = dot4(ldg4(inp + o11 * ld + c), g);
+                gix += s * tp.wy1; giy += s * tp.wx1;
+            }
         }
         if (ddeform) {
             if (seg > 1) {
@@ -180,10 +211,11 @@ __global__ void __launch_bounds__(256) k_grid_sample_bwd(const float* __restrict
                         giy += __shfl_xor_sync(0xffffffffu, giy, o);
                     }
                 }
-                if (((threadIdx.x & 31) & (seg - 1)) != 0) return;
+                if (((threadIdx.x & 31) & (seg - 1)) != 0) continue;
             }
-            scatter_grid_grad(ddeform, n, h0, w0, ho, wo, h, w, mode, gix * 0.5f * (float)(w - 1),
-                              giy * 0.5f * (float)(h - 1));
+            if (inside)
+                scatter_grid_grad(ddeform, n, h0, w0, ho, wo, h, w, mode, gix * 0.5f * (float)(w - 1),
+                                  giy * 0.5f * (float)(h - 1));
         }
     }
 }
@@ -196,17 +228,18 @@ MK_EXPORT int mk_grid_sample_bwd(const float* inp, int B, int h, int w, int Cp, 
     const int cv = Cp / 4;
     const long long total = (long long)B * d * h * w * cv;
     if (total == 0) return 0;
-    // segmented shuffle reduction needs (a) cv a power of two <= 32 or a multiple of 32, and (b) no partial warps:
-    // total is a multiple of cv, so with cv | 32 or 32 | cv whole pixels/lane-groups never straddle the loop tail
-    // as long as total % 32 == 0; otherwise fall back to per-thread atomics (seg = 1).
+    const Patch pt = make_patch(h, w, cv);
+    // segmented shuffle reduction over the channel lanes of a pixel: cv a power of two <= 32 (a pixel = `cv` aligned
+    // lanes) or a multiple of 32 (whole warps per pixel); otherwise per-thread atomics (seg = 1).  Patches hold a
+    // multiple of 32 items, so warps are never partial.
     int seg = 1;
     if ((cv & (cv - 1)) == 0 && cv <= 32) seg = cv;
     else if (cv % 32 == 0) seg = 32;
-    if (total % 32 != 0) seg = 1;
-    MK_REQUIRE(total < (1LL << 31), "mk_grid_sample_bwd: more than 2^31 work items");
-    k_grid_sample_bwd<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        inp, h, w, cv, ld, deform, d, h0, w0, mode, dout, ldo, dinp, lddi, ddeform, seg, total, make_fastdiv(cv),
-        make_fastdiv(w), make_fastdiv(h));
+    const long long blocks = (long long)B * d * pt.tiles_x * pt.tiles_y;
+    MK_REQUIRE(blocks < (1LL << 31), "mk_grid_sample_bwd: extent too large");
+    k_grid_sample_bwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        inp, h, w, cv, ld, deform, d, h0, w0, mode, dout, ldo, dinp, lddi, ddeform, seg, pt, make_fastdiv(cv),
+        make_fastdiv(pt.tiles_x), make_fastdiv(pt.tiles_y));
     return mk_check_launch("mk_grid_sample_bwd");
 }
 

@@ -3,13 +3,18 @@
 // GEMM view: D[M = co][N = ci] accumulated over K = pixels.  In NHWC both operands have their M/N index (channels)
 // contiguous and the contraction index (pixels) strided, i.e. they are "MN-major" UMMA operands - tcgen05 takes them
 // directly (a_major = b_major = 1 in the instruction descriptor), so no transposed copies of the activations exist:
-//   * A stage = four 4-D TMA boxes {32 co, TW, TH, TN} of dY (32 pixels each), B stage = up to four boxes
-//     {32 ci, TW, TH, TN} of X shifted by the filter tap; out-of-bounds pixels are zero-filled = conv padding.
-//     Each box is [32 pixels][128 B] in the 128B swizzle with 32-byte atoms (TMA SWIZZLE_128B_ATOM_32B ==
-//     UMMA SWIZZLE_128B_BASE32B, the only MN-major layout 32-bit operands may use) = one MN block of the
-//     canonical layout ((8,n),(4,k)) with LBO = box size (4096 B), SBO = 512 B (4 pixel rows).
-//   * 4 x tcgen05.mma.kind::tf32 (K = 8 pixels each) per stage; accumulator [128 co][<=128 ci] fp32 in TMEM.
-//   * grid = (co tiles, taps x ci tiles, pixel splits); splits combine with fp32 atomics (red) into the packed
+//   * operand tile = 4-D TMA boxes {32 ch, TW, TH, TN} of PC = 64 pixels; each box is [64 pixels][128 B] in the 128B
+//     swizzle with 32-byte atoms (TMA SWIZZLE_128B_ATOM_32B == UMMA SWIZZLE_128B_BASE32B, the only MN-major layout
+//     32-bit operands may use) = one MN block of the canonical layout ((8,n),(4,k)) with LBO = box size, SBO = 512 B
+//     (4 pixel rows).  Out-of-bounds pixels are zero-filled by the TMA unit = the convolution's zero padding.
+//   * ONE CTA owns a pixel range and ALL filter taps that fit in TMEM (taps x round16(ci) <= 512 accumulator
+//     columns): the dY tile of a pixel chunk is loaded once (A ring) and multiplied with the R*S shifted X tiles
+//     (B ring), each tap accumulating into its own TMEM column range.  The previous version ran one tap per CTA:
+//     dY was fetched R*S times, 4 dY boxes were staged whatever Cout was, and the full-resolution small-channel
+//     layers (24 -> 24 @ 64x64 x 32 frames) took 150 us; now they are a single pass over X and dY.
+//   * only the 32-channel boxes that exist are staged (ceil(co/32) A boxes, ceil(ci/32) B boxes).  The MMA still runs
+//     M = 128: accumulator rows beyond the staged boxes are products of stale shared memory and are never read.
+//   * grid = (co tiles, tap groups x ci tiles, pixel splits); splits combine with fp32 atomics (red) into the packed
 //     gradient, whose layout [tap][Cin_p][Cout_p] makes the epilogue's per-column writes coalesced across lanes.
 #include "tc_common.cuh"
 #include "../../include/monkey_b200.h"
@@ -17,15 +22,16 @@
 namespace {
 using namespace mk_tc;
 
-constexpr int PC = 32;            // pixels per stage
-constexpr int BOX_BYTES = PC * 128;
-constexpr int WSTAGES = 6;
-constexpr int WSTAGE_BYTES = 8 * BOX_BYTES;  // 4 A boxes + 4 B boxes
-constexpr int WSMEM_BYTES = WSTAGES * WSTAGE_BYTES + 1024 + 256;
+constexpr int PC = 64;                 // pixels per chunk (GEMM K per pipeline step)
+constexpr int BOX_BYTES = PC * 128;    // one 32-channel box
+constexpr int MAX_A = 4, MAX_B = 12;   // ring depths (upper bounds)
+constexpr int WSMEM_MAX = 227 * 1024;
 
 struct WgTcP {
     int N, Ho, Wo, Cout_p, Cin_p, R, S, pad;
     int TW, TH, TN, tilesW, tilesH, nchunks, chunks_per_split, n_ci_tiles;
+    int taps_per_cta, n_tap_groups, npad;   // npad = accumulator columns per tap (round16 of the ci tile)
+    int na_max, nb_max, a_slots, b_slots, tmem_cols;
     float* dw;
 };
 
@@ -43,33 +49,41 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
                                                   const __grid_constant__ CUtensorMap tmX, const WgTcP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WSTAGES * WSTAGE_BYTES);
-    uint64_t* empty = full + WSTAGES;
-    uint64_t* tmem_full = empty + WSTAGES;
+    const int A_SLOT = p.na_max * BOX_BYTES, B_SLOT = p.nb_max * BOX_BYTES;
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + p.a_slots * A_SLOT;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + p.b_slots * B_SLOT);
+    uint64_t* a_empty = a_full + MAX_A;
+    uint64_t* b_full = a_empty + MAX_A;
+    uint64_t* b_empty = b_full + MAX_B;
+    uint64_t* tmem_full = b_empty + MAX_B;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int co0 = blockIdx.x * 128;
-    const int tap = blockIdx.y / p.n_ci_tiles, ci0 = (blockIdx.y % p.n_ci_tiles) * 128;
-    const int r = tap / p.S, s = tap - r * p.S;
+    const int tg = blockIdx.y / p.n_ci_tiles, ci0 = (blockIdx.y % p.n_ci_tiles) * 128;
+    const int tap_begin = tg * p.taps_per_cta;
+    const int ntaps = min(p.taps_per_cta, p.R * p.S - tap_begin);
+    const int m_this = min(128, p.Cout_p - co0);
     const int n_this = min(128, p.Cin_p - ci0);          // multiple of 4; the MMA runs on the next multiple of 16
-    const int nb = (n_this + 31) >> 5;                   // B boxes actually needed
+    const int na = (m_this + 31) >> 5, nb = (n_this + 31) >> 5;
     const int q0 = blockIdx.z * p.chunks_per_split;
     const int q1 = min(p.nchunks, q0 + p.chunks_per_split);
-    const int niter = q1 - q0;
+    const int nq = q1 - q0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDy) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < WSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < MAX_A; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < MAX_B; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(128u)
+                     "r"((uint32_t)p.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -79,67 +93,88 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        // ===================================================================== TMA producer
         if (elect_one()) {
-            for (int it = 0; it < niter; ++it) {
-                const int stage = it % WSTAGES;
-                const uint32_t phase = (it / WSTAGES) & 1;
-                int q = q0 + it;
+            int bi = 0;
+            for (int qi = 0; qi < nq; ++qi) {
+                int q = q0 + qi;
                 const int tw = q % p.tilesW; q /= p.tilesW;
                 const int th = q % p.tilesH; q /= p.tilesH;
                 const int w0 = tw * p.TW, h0 = th * p.TH, n0 = q * p.TN;
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* a = smem + stage * WSTAGE_BYTES;
-                mbar_expect_tx(&full[stage], (4 + nb) * BOX_BYTES);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) tma_load_4d(a + j * BOX_BYTES, &tmDy, &full[stage], co0 + j * 32, w0, h0, n0);
-                for (int j = 0; j < nb; ++j)
-                    tma_load_4d(a + (4 + j) * BOX_BYTES, &tmX, &full[stage], ci0 + j * 32, w0 + s - p.pad, h0 + r - p.pad,
-                                n0);
+                const int as = qi % p.a_slots;
+                mbar_wait(&a_empty[as], ((qi / p.a_slots) & 1) ^ 1);
+                uint8_t* a = a_ring + as * A_SLOT;
+                mbar_expect_tx(&a_full[as], na * BOX_BYTES);
+                for (int j = 0; j < na; ++j) tma_load_4d(a + j * BOX_BYTES, &tmDy, &a_full[as], co0 + j * 32, w0, h0, n0);
+                for (int t = 0; t < ntaps; ++t, ++bi) {
+                    const int tap = tap_begin + t;
+                    const int r = tap / p.S, s = tap - r * p.S;
+                    const int bs = bi % p.b_slots;
+                    mbar_wait(&b_empty[bs], ((bi / p.b_slots) & 1) ^ 1);
+                    uint8_t* b = b_ring + bs * B_SLOT;
+                    mbar_expect_tx(&b_full[bs], nb * BOX_BYTES);
+                    for (int j = 0; j < nb; ++j)
+                        tma_load_4d(b + j * BOX_BYTES, &tmX, &b_full[bs], ci0 + j * 32, w0 + s - p.pad, h0 + r - p.pad,
+                                    n0);
+                }
             }
         }
     } else if (warp == 1) {
-        // M = 128 (co), N = n_this (ci), both operands MN-major
+        // ===================================================================== MMA issuer
+        // M = 128 (co), N = round16(n_this) (ci), both operands MN-major; tap t accumulates at column t * npad
         const uint32_t idesc = umma_idesc_tf32(128, (n_this + 15) & ~15) | (1u << 15) | (1u << 16);
-        for (int it = 0; it < niter; ++it) {
-            const int stage = it % WSTAGES;
-            const uint32_t phase = (it / WSTAGES) & 1;
-            mbar_wait(&full[stage], phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-                const uint8_t* a = smem + stage * WSTAGE_BYTES;
-                const uint64_t adesc = umma_desc_mn(a), bdesc = umma_desc_mn(a + 4 * BOX_BYTES);
+        int bi = 0;
+        for (int qi = 0; qi < nq; ++qi) {
+            const int as = qi % p.a_slots;
+            mbar_wait(&a_full[as], (qi / p.a_slots) & 1);
+            for (int t = 0; t < ntaps; ++t, ++bi) {
+                const int bs = bi % p.b_slots;
+                mbar_wait(&b_full[bs], (bi / p.b_slots) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_mn(a_ring + as * A_SLOT);
+                    const uint64_t bdesc = umma_desc_mn(b_ring + bs * B_SLOT);
+                    const uint32_t dcol = tmem_base + (uint32_t)(t * p.npad);
 #pragma unroll
-                for (int k = 0; k < PC / 8; ++k)  // 8 pixel rows = 1024 B = 64 sixteen-byte units
-                    umma_tf32(tmem_base, adesc + 64 * k, bdesc + 64 * k, idesc, (it | k) ? 1u : 0u);
-                umma_commit(&empty[stage]);
-                if (it == niter - 1) umma_commit(tmem_full);
+                    for (int k = 0; k < PC / 8; ++k)  // 8 pixel rows = 1024 B = 64 sixteen-byte units
+                        umma_tf32(dcol, adesc + 64 * k, bdesc + 64 * k, idesc, (qi | k) ? 1u : 0u);
+                    umma_commit(&b_empty[bs]);
+                    if (t == ntaps - 1) {
+                        umma_commit(&a_empty[as]);
+                        if (qi == nq - 1) umma_commit(tmem_full);
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
-    } else if (warp >= 4 && niter > 0) {
+    } else if (warp >= 4 && nq > 0) {
+        // ===================================================================== epilogue
         const int q = warp & 3;
         const int co = co0 + q * 32 + lane;
         const bool valid = co < p.Cout_p;
         mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* base = p.dw + ((long long)tap * p.Cin_p + ci0) * p.Cout_p + co;
-        for (int c = 0; c < n_this; c += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            if (!valid) continue;
+        for (int t = 0; t < ntaps; ++t) {
+            float* base = p.dw + ((long long)(tap_begin + t) * p.Cin_p + ci0) * p.Cout_p + co;
+            for (int c = 0; c < n_this; c += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.npad + c), v);
+                if (!valid) continue;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                if (c + j >= n_this) break;  // ragged Cin_p: the extra columns are products with TMA zero fill
-                float* dst = base + (long long)(c + j) * p.Cout_p;
-                if (gridDim.z == 1) *dst = v[j];
-                else atomicAdd(dst, v[j]);
+                for (int j = 0; j < 16; ++j) {
+                    if (c + j >= n_this) break;  // ragged Cin_p: the extra columns are products with TMA zero fill
+                    float* dst = base + (long long)(c + j) * p.Cout_p;
+                    if (gridDim.z == 1) *dst = v[j];
+                    else atomicAdd(dst, v[j]);
+                }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                     : "memory");
     }
 }
 
@@ -164,13 +199,43 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
     p.nchunks = p.tilesW * p.tilesH * ((N + p.TN - 1) / p.TN);
     p.n_ci_tiles = (Cin_p + 127) / 128;
     const int co_tiles = (Cout_p + 127) / 128;
-    const long long tiles = (long long)co_tiles * p.n_ci_tiles * R * S;
-    long long splits = mk_cdiv(2LL * mk_num_sms(), tiles);
-    if (splits > p.nchunks / 4) splits = p.nchunks / 4;  // at least 4 chunks (128 pixels) per CTA
+    // accumulator columns per tap, taps per CTA (TMEM has 512 columns)
+    const int n_tile = Cin_p < 128 ? Cin_p : 128;
+    p.npad = (n_tile + 15) & ~15;
+    p.taps_per_cta = 512 / p.npad < R * S ? 512 / p.npad : R * S;
+    p.n_tap_groups = (R * S + p.taps_per_cta - 1) / p.taps_per_cta;
+    p.taps_per_cta = (R * S + p.n_tap_groups - 1) / p.n_tap_groups;  // balance the groups (9 taps, 4 fit -> 3+3+3)
+    p.n_tap_groups = (R * S + p.taps_per_cta - 1) / p.taps_per_cta;
+    const int cols = p.taps_per_cta * p.npad;
+    p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+    p.na_max = ((Cout_p < 128 ? Cout_p : 128) + 31) / 32;
+    p.nb_max = (n_tile + 31) / 32;
+    // pixel splits: fill the machine (about one CTA per SM - the 512-column case allows no second resident CTA)
+    const long long tiles = (long long)co_tiles * p.n_ci_tiles * p.n_tap_groups;
+    const int sms = mk_num_sms();
+    long long splits = mk_cdiv((p.tmem_cols <= 256 ? 2LL : 1LL) * sms, tiles);
+    if (splits > p.nchunks) splits = p.nchunks;
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
     p.chunks_per_split = (int)mk_cdiv(p.nchunks, splits);
     splits = mk_cdiv(p.nchunks, p.chunks_per_split);
+    // rings: never deeper than the loops; within ~100 KB when two CTAs can share an SM, ~200 KB otherwise
+    const int budget = (p.tmem_cols <= 256 && tiles * splits > sms) ? 100 * 1024 : 200 * 1024;
+    const int a_slot = p.na_max * BOX_BYTES, b_slot = p.nb_max * BOX_BYTES;
+    p.a_slots = p.chunks_per_split < 2 ? 1 : 2;
+    int bs = (budget - p.a_slots * a_slot) / b_slot;
+    const long long b_loads = (long long)p.chunks_per_split * p.taps_per_cta;
+    if (bs > MAX_B) bs = MAX_B;
+    if (bs > b_loads) bs = (int)b_loads;
+    if (bs < 2) bs = 2;
+    p.b_slots = bs;
+    // the M = 128 MMA reads four 32-channel A boxes whatever Cout is: the rows beyond the staged boxes are never
+    // used, but the addresses must lie inside this CTA's shared-memory allocation
+    int ring_bytes = p.a_slots * a_slot + p.b_slots * b_slot + 512 /*barriers*/;
+    const int a_reach = (p.a_slots - 1) * a_slot + 4 * BOX_BYTES;
+    if (ring_bytes < a_reach) ring_bytes = a_reach;
+    const int smem_bytes = ring_bytes + 1024 /*align*/;
+    MK_REQUIRE(smem_bytes <= WSMEM_MAX, "mk_conv2d_wgrad_tc: shared memory plan exceeds 227 KB (%d)", smem_bytes);
 
     CUtensorMap tmDy, tmX;
     cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
@@ -194,7 +259,7 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
     cudaStream_t st = (cudaStream_t)stream;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM_MAX);
         if (e != cudaSuccess) { mk_set_error("mk_conv2d_wgrad_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_set = true;
     }
@@ -202,7 +267,7 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
         cudaError_t e = cudaMemsetAsync(dwpack, 0, sizeof(float) * (size_t)R * S * Cin_p * Cout_p, st);
         if (e != cudaSuccess) { mk_set_error("mk_conv2d_wgrad_tc memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    dim3 grid((unsigned)co_tiles, (unsigned)(R * S * p.n_ci_tiles), (unsigned)splits);
-    k_wgrad_tc<<<grid, 256, WSMEM_BYTES, st>>>(tmDy, tmX, p);
+    dim3 grid((unsigned)co_tiles, (unsigned)(p.n_tap_groups * p.n_ci_tiles), (unsigned)splits);
+    k_wgrad_tc<<<grid, 256, smem_bytes, st>>>(tmDy, tmX, p);
     return mk_check_launch("mk_conv2d_wgrad_tc");
 }

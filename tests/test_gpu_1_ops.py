@@ -232,7 +232,10 @@ def test_instancenorm_leaky_pool(norm):
 # ------------------------------------------------------------------------------------------------------ sampling
 @pytest.mark.parametrize('c,h,h0,mode,d', [(3, 16, 16, 'nearest', 1), (16, 8, 16, 'nearest', 2),
                                             (32, 4, 16, 'trilinear', 1), (128, 2, 16, 'nearest', 1),
-                                            (8, 32, 16, 'trilinear', 1), (1024, 2, 8, 'nearest', 1)])
+                                            (8, 32, 16, 'trilinear', 1), (1024, 2, 8, 'nearest', 1),
+                                            (20, 13, 16, 'nearest', 1),     # 5 channel vectors, partial 16x16 patches
+                                            (68, 9, 16, 'trilinear', 2),    # 17 channel vectors: ragged last item pass
+                                            (64, 24, 16, 'nearest', 1)])    # 3x3 patches of 8x8, 4 items per thread
 def test_grid_sample(c, h, h0, mode, d):
     o = ops()
     torch.manual_seed(c + h)
