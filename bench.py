@@ -395,15 +395,16 @@ def kernel_bench(device, pk):
     """grid_sample HBM roofline on the large vox-full pyramid levels: algorithmic bytes
     4*(B*C*h*w + 2*B*d*h*w + B*d*C*h*w) / CUDA-event time, L2 flushed between launches."""
     from monkey_net_b200 import lib
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import prof_kernels
     st = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    res = {}
+    res = {'deformation': 'identity + smooth displacement (8x8 noise, bicubic, amplitude 0.3) at 256x256, nearest '
+                          'resize to the level'}
     B, d = 16, 1
     for (C, h) in ((64, 128), (128, 64), (4, 256)):
         inp = torch.rand(B, h, h, C, device=device)
-        ys, xs = torch.meshgrid(torch.linspace(-1, 1, 256, device=device), torch.linspace(-1, 1, 256, device=device),
-                                indexing='ij')
-        deform = (torch.stack([xs, ys], -1)[None] + 0.05 * torch.randn(B * d, 256, 256, 2, device=device)).contiguous()
+        deform = prof_kernels.smooth_deformation(B * d, 256, device)  # smooth, network-like flow field
         out = torch.empty(B * d, h, h, C, device=device)
         times = []
         for it in range(8):

@@ -1,6 +1,6 @@
 """Launch the hot kernels on representative shapes (for `ncu --set full` captures and quick CUDA-event timings).
 
-    python tools/prof_kernels.py [grid|conv|all]
+    python tools/prof_kernels.py [grid|conv|convtc|all]
 Shapes: grid_sample on the large vox-full pyramid levels (B=16: 3x256^2, 64x128^2, 128x64^2);
 conv on shapes.yaml / taichi.yaml layers at batch 32.  Prints one line per kernel with ms and achieved GB/s or TFLOP/s.
 """
@@ -26,6 +26,18 @@ def timeit(fn, flush, reps=5):
     return sum(ts) / len(ts)
 
 
+def smooth_deformation(n, res, device, amp=0.3, coarse=8, seed=0):
+    """identity grid + a smooth displacement field (coarse x coarse gaussian noise, bilinearly upsampled), amplitude
+    `amp` in normalised units: the shape of the fields the dense-motion network produces (predicted at low resolution,
+    sums of a few keypoint shifts), unlike per-pixel white noise which no layer of the model can emit."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, res), torch.linspace(-1, 1, res), indexing='ij')
+    base = torch.stack([xs, ys], -1)[None]
+    disp = torch.nn.functional.interpolate(torch.randn(n, 2, coarse, coarse, generator=g), size=(res, res),
+                                           mode='bicubic', align_corners=True).permute(0, 2, 3, 1)
+    return (base + amp * disp / disp.abs().max()).contiguous().to(device)
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     dev = torch.device('cuda', 0)
@@ -35,9 +47,7 @@ def main():
         B, d = 16, 1
         for C, h in ((4, 256), (64, 128), (128, 64), (256, 32)):
             inp = torch.rand(B, h, h, C, device=dev)
-            ys, xs = torch.meshgrid(torch.linspace(-1, 1, 256, device=dev), torch.linspace(-1, 1, 256, device=dev),
-                                    indexing='ij')
-            deform = (torch.stack([xs, ys], -1)[None] + 0.05 * torch.randn(B, 256, 256, 2, device=dev)).contiguous()
+            deform = smooth_deformation(B, 256, dev)
             out = torch.empty(B, h, h, C, device=dev)
             dinp, ddef = torch.zeros_like(inp), torch.zeros_like(deform)
             lc = 3 if C == 4 else C
@@ -66,5 +76,29 @@ def main():
             print('conv3x3 wgrad %4d->%4d @%dx%d N=%d: %.4f ms  %.2f TFLOP/s' % (cin, cout, h, h, N, ms, fl / ms / 1e9))
 
 
+def conv_tc_cases(dev, st, flush):
+    """tensor-core conv forward + wgrad on layers of taichi@256 (B=8) and shapes@64 (B=32)."""
+    for N, h, cin, cout, k, pad in ((8, 256, 48, 48, 3, 1), (8, 58, 256, 128, 4, 3), (16, 128, 64, 256, 3, 1),
+                                    (32, 64, 24, 24, 3, 1)):
+        x = torch.randn(N, h, h, cin, device=dev)
+        w = torch.randn(cout, cin, 1, k, k, device=dev) * 0.05
+        ho = h + 2 * pad - k + 1
+        wt = torch.empty(k * k * cin * cout, device=dev)
+        lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, 2, wt.data_ptr(), None, None, st)
+        y = torch.empty(N, ho, ho, cout, device=dev)
+        dw = torch.empty(k * k * cin * cout, device=dev)
+        fl = 2.0 * N * ho * ho * cin * cout * k * k
+        ms = timeit(lambda: lib.call('mk_conv2d_tc', x.data_ptr(), N, h, h, cin, cin, 0, wt.data_ptr(), k, k, pad, None,
+                                     None, None, 0, 0, 0.0, y.data_ptr(), cout, cout, st), flush)
+        print('conv_tc  fwd   %4d->%4d k%d @%dx%d N=%d: %.4f ms  %.1f TFLOP/s' % (cin, cout, k, h, h, N, ms, fl / ms / 1e9))
+        ms = timeit(lambda: lib.call('mk_conv2d_wgrad_tc', x.data_ptr(), N, h, h, cin, cin, y.data_ptr(), cout, cout, k, k,
+                                     pad, dw.data_ptr(), st), flush)
+        print('conv_tc  wgrad %4d->%4d k%d @%dx%d N=%d: %.4f ms  %.1f TFLOP/s' % (cin, cout, k, h, h, N, ms, fl / ms / 1e9))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'convtc':
+        _dev = torch.device('cuda', 0)
+        conv_tc_cases(_dev, torch.cuda.current_stream().cuda_stream, torch.empty(256 << 20, dtype=torch.uint8, device=_dev))
+        sys.exit(0)
     main()
