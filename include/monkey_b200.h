@@ -26,6 +26,9 @@ extern "C" {
 const char* mk_last_error(void);
 int mk_version(void);
 int mk_fill_zero(void* ptr, long long bytes, void* stream);
+/* benchmark helper: evict the L2 by READING `bytes` (>= 2x the 126 MB L2) of `buf`; unlike a memset it leaves no
+ * dirty lines behind to be written back during the timed kernel.  `buf` must be 16-byte aligned. */
+int mk_l2_evict(const void* buf, long long bytes, void* stream);
 
 /* ---- layout edge: reference NCDHW tensors <-> internal NHWC (SURVEY 8(b) "convert only at this edge") ----
  * src is a 5-D (B,C,D,H,W) tensor with arbitrary element strides; `step` implements the nearest down-scale

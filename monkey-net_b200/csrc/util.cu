@@ -36,6 +36,26 @@ MK_EXPORT int mk_fill_zero(void* ptr, long long bytes, void* stream) {
     return 0;
 }
 
+// L2 eviction for benchmarks: READ a buffer larger than the 126 MB L2.  A memset of that buffer also evicts, but it
+// leaves the L2 full of DIRTY lines whose write-back then competes with the kernel being timed (a 136 MB
+// grid_sample measured 40-53 us after a memset flush, 27 us under ncu's own cache control); clean lines cost nothing
+// to replace.
+__global__ void __launch_bounds__(256) k_l2_evict(const float4* __restrict__ buf, long long n4, float* __restrict__ sink) {
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldcs(buf + i);
+        acc += v.x + v.y + v.z + v.w;
+    }
+    if (acc == 1.2345678e33f) *sink = acc;  // never true for a zero buffer; keeps the loads alive
+}
+
+MK_EXPORT int mk_l2_evict(const void* buf, long long bytes, void* stream) {
+    if (bytes < 32) return 0;
+    float* sink = reinterpret_cast<float*>(const_cast<void*>(buf));
+    k_l2_evict<<<8 * mk_num_sms(), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(buf), bytes / 16, sink);
+    return mk_check_launch("mk_l2_evict");
+}
+
 // ------------------------------------------------------------------------------------------------ NCDHW -> NHWC
 // One thread per (output pixel, physical channel).  Reads are strided on the NCDHW side (the channel planes are
 // far apart); the tensors that cross this edge are images (C = 3) so the traffic is negligible next to the convs.

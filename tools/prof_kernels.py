@@ -17,7 +17,7 @@ def timeit(fn, flush, reps=5):
     st = torch.cuda.current_stream().cuda_stream
     ts = []
     for i in range(reps + 2):
-        lib.call('mk_fill_zero', flush.data_ptr(), flush.numel(), st)
+        lib.call('mk_l2_evict', flush.data_ptr(), flush.numel(), st)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); fn(); e.record()
         torch.cuda.synchronize()
@@ -42,7 +42,7 @@ def main():
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     dev = torch.device('cuda', 0)
     st = torch.cuda.current_stream().cuda_stream
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=dev)
     if what in ('grid', 'all'):
         B, d = 16, 1
         for C, h in ((4, 256), (64, 128), (128, 64), (256, 32)):
@@ -99,6 +99,6 @@ def conv_tc_cases(dev, st, flush):
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'convtc':
         _dev = torch.device('cuda', 0)
-        conv_tc_cases(_dev, torch.cuda.current_stream().cuda_stream, torch.empty(256 << 20, dtype=torch.uint8, device=_dev))
+        conv_tc_cases(_dev, torch.cuda.current_stream().cuda_stream, torch.zeros(256 << 20, dtype=torch.uint8, device=_dev))
         sys.exit(0)
     main()
