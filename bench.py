@@ -155,7 +155,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=device)
+        import datetime
+        # a rank that dies or diverges must fail the run in minutes, not hang the box for NCCL's default 10
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=180))
     lib.load()
     from monkey_net_b200 import ops as mkops
     conv_mode = mkops.CONV_MODE
@@ -183,6 +185,7 @@ def run_ours(args):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         for s, e in evs:
+            lib.call('mk_fill_zero', flush.data_ptr(), flush.numel(), torch.cuda.current_stream().cuda_stream)
             lib.call('mk_l2_evict', flush.data_ptr(), flush.numel(), torch.cuda.current_stream().cuda_stream)
             s.record()
             step_fn()
@@ -212,7 +215,7 @@ def run_ours(args):
     if trainer.graph is not None:   # kernels recorded into the CUDA graph at capture time, replayed every step
         launches = trainer.kernels_per_step * args.steps
     else:
-        launches = lib.launches() - n0 - args.steps  # minus the L2-flush memsets
+        launches = lib.launches() - n0 - 2 * args.steps  # minus the L2-flush memset + read pass
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
@@ -221,7 +224,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel family (implicit-GEMM convolutions): device time by CUDA events around
     # every conv launch on the launching stream, algorithmic FLOPs from the oracle's conv hooks
     conv_ms = None
-    if rank == 0:
+    n_conv = 0
+    if True:  # EVERY rank runs this pass: the iteration contains collectives (BN statistics, gradient all-reduce)
         names = ('mk_conv2d', 'mk_conv2d_wgrad', 'mk_conv2d_tc', 'mk_conv2d_wgrad_tc')
         spans = []
         orig = lib.call
@@ -247,9 +251,7 @@ def run_ours(args):
         dist.barrier()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        _exit_rank()
     pk = peaks()
     flops = conv_flops_per_step(cfg, args.res, B)
     frames = B * world * args.steps
@@ -263,7 +265,7 @@ def run_ours(args):
                                'frame, fwd+bwd+Adam for G, KP and D' % (args.config, B, args.res, args.res),
                    'global_batch': B * world, 'parallelism': 'dp%d' % world,
                    'cuda_graph': trainer.graph is not None, 'conv_mode': conv_mode,
-                   'l2': 'evicted between timed steps (256 MiB read pass, outside the per-step event pairs)',
+                   'l2': 'flushed between timed steps: 256 MiB memset (write) followed by a read pass over the same buffer so no dirty lines are left to be written back inside the timed region; both outside the per-step event pairs',
                    'conv_gflop_per_sample': flops['train_step_per_sample'] / 1e9},
         'e2e': {'value': frames / (ms_e2e / 1e3), 'unit': 'frames/s',
                 'h2d_bytes_per_step': sum(v.numel() * 4 for v in host.values()),
@@ -284,6 +286,23 @@ def run_ours(args):
         out['kernels'] = kernel_bench(device, pk)
     if not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_baseline(args, cfg)
+    if world == 1 and conv_mode == 'tf32' and not args.no_kernel_bench:
+        # the same step with the EXACT fp32 (FFMA) convolutions, for readers who want the no-TF32 number
+        mkops.set_conv_mode('fp32')
+        try:
+            g2, d2, k2 = build_nets(cfg, device)
+            for m in (g2, d2, k2):
+                m.train()
+            t2 = train_step.GraphedTrainer(k2, g2, d2, tp, use_graph=use_graph)
+            for _ in range(3):
+                t2.step(resident)
+            n2 = max(3, args.steps // 2)
+            ms2 = timed(lambda: t2.step(resident), n2)
+            out['fp32_exact'] = {'value': B * n2 / (ms2 / 1e3), 'unit': 'frames/s', 'ms_per_step': ms2 / n2,
+                                 'note': 'MONKEY_B200_CONV=fp32: every convolution on the exact FFMA kernels'}
+            del t2, g2, d2, k2
+        finally:
+            mkops.set_conv_mode('tf32')
     if world == 1 and not args.no_transfer:
         del trainer, gen, disc, kp
         torch.cuda.empty_cache()
@@ -291,7 +310,17 @@ def run_ours(args):
                                              cpu=not args.no_cpu_baseline)
     print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        _exit_rank()
+
+
+def _exit_rank():
+    """Multi-rank exit without NCCL teardown ordering: rank 0 goes on to CPU-side work (FLOP count, CPU baseline) for
+    up to a minute after the other ranks are done, and ncclCommDestroy on one side waiting for a peer that has already
+    left hung the launcher (observed at N=2).  All collectives are complete and synchronised at this point, so the
+    processes flush and leave; the driver reads rank 0's JSON line."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def transfer_bench(device, config, res, batch, d, steps, warmup, cpu=True):
@@ -323,6 +352,7 @@ def transfer_bench(device, config, res, batch, d, steps, warmup, cpu=True):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         torch.cuda.synchronize()
         for s_, e_ in evs:
+            lib.call('mk_fill_zero', flush.data_ptr(), flush.numel(), torch.cuda.current_stream().cuda_stream)
             lib.call('mk_l2_evict', flush.data_ptr(), flush.numel(), torch.cuda.current_stream().cuda_stream)
             s_.record(); fn(); e_.record()
         torch.cuda.synchronize()
@@ -408,6 +438,7 @@ def kernel_bench(device, pk):
         out = torch.empty(B * d, h, h, C, device=device)
         times = []
         for it in range(8):
+            lib.call('mk_fill_zero', flush.data_ptr(), flush.numel(), st)
             lib.call('mk_l2_evict', flush.data_ptr(), flush.numel(), st)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -537,7 +568,8 @@ def run_transfer(args):
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=device)
+        import datetime
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=180))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -562,7 +594,7 @@ def run_transfer(args):
             out['cpu_baseline'] = r['cpu_baseline']
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        _exit_rank()
 
 
 if __name__ == '__main__':

@@ -83,6 +83,37 @@ class GradSync:
                 off += n
 
 
+class FlatGradSync:
+    """Gradient averaging with ZERO copies: the `.grad` of every parameter of the group is a view into one flat
+    buffer (like DDP's gradient_as_bucket_view), so data-parallel training needs exactly one all-reduce per optimiser
+    step - `sync()` between `backward()` and `optimizer.step()` - instead of one small collective per parameter.
+    Requires `optimizer.zero_grad(set_to_none=False)` (torch 0.4.1's zero_grad, which the reference was written for,
+    zeroes in place too).  Deterministic layout: parameters in `module.parameters()` order."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def intact(self):
+        base = self.flat.data_ptr()
+        return all(p.grad is not None and base <= p.grad.data_ptr() < base + self.flat.numel() * 4 for p in self.params)
+
+    def sync(self):
+        w = world()
+        if w == 1:
+            return
+        assert self.intact(), 'a gradient view was replaced (zero_grad(set_to_none=True)?)'
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self.flat.mul_(1.0 / w)
+
+
 def shard_batch(x, dim=0):
     """This rank's contiguous share of a global batch (DataParallel scatter semantics, train.py:104-110)."""
     w, r = world(), rank()

@@ -55,24 +55,29 @@ def make_optimizers(generator, discriminator, kp_detector, lr):
     return mk(generator), mk(discriminator), mk(kp_detector)
 
 
-def train_iteration(generator_full_par, discriminator_full_par, optimizers, train_params, x):
-    """One loop body of train.py:110-136.  Returns (generator loss tensors, discriminator loss tensors)."""
+def train_iteration(generator_full_par, discriminator_full_par, optimizers, train_params, x, grad_sync=None):
+    """One loop body of train.py:110-136.  Returns (generator loss tensors, discriminator loss tensors).
+    `grad_sync` = (sync_g, sync_d, sync_kp) FlatGradSync objects for data-parallel runs (one all-reduce per optimiser
+    step, gradients zeroed in place like torch 0.4.1 did); None = the reference's code verbatim."""
     opt_g, opt_d, opt_kp = optimizers
+    keep = grad_sync is not None
+    zero = (lambda o: o.zero_grad(set_to_none=False)) if keep else (lambda o: o.zero_grad())
+    sync = (lambda i: grad_sync[i].sync()) if keep else (lambda i: None)
     out = generator_full_par(x)
     loss_values = [val.mean() for val in out[:-2]]
     generated, kp_joined = out[-2], out[-1]
     loss = sum(loss_values)
     loss.backward(retain_graph=not train_params['detach_kp_discriminator'])
-    opt_g.step(); opt_g.zero_grad(); opt_d.zero_grad()
+    sync(0); opt_g.step(); zero(opt_g); zero(opt_d)
     if train_params['detach_kp_discriminator']:
-        opt_kp.step(); opt_kp.zero_grad()
+        sync(2); opt_kp.step(); zero(opt_kp)
     g_vals = loss_values
     loss_values = [val.mean() for val in discriminator_full_par(x, kp_joined, generated)]
     loss = sum(loss_values)
     loss.backward()
-    opt_d.step(); opt_d.zero_grad()
+    sync(1); opt_d.step(); zero(opt_d)
     if not train_params['detach_kp_discriminator']:
-        opt_kp.step(); opt_kp.zero_grad()
+        sync(2); opt_kp.step(); zero(opt_kp)
     return g_vals, loss_values
 
 
@@ -100,13 +105,23 @@ class GraphedTrainer:
         mk = lambda m: torch.optim.Adam(m.parameters(), lr=train_params['lr'], betas=(0.5, 0.999),
                                         capturable=bool(use_graph))
         self.optimizers = (mk(generator), mk(discriminator), mk(kp_detector))
+        self.grad_sync = None
+        from . import dist as mkdist
+        if mkdist.world() > 1:
+            # data parallel: ONE all-reduce per optimiser step over a flat gradient buffer instead of the wrapper's
+            # per-parameter hooks (about 200 latency-bound collectives per iteration)
+            import sync_batchnorm.replicate as rep
+            rep.HOOKS_ENABLED = False
+            self.grad_sync = (mkdist.FlatGradSync(generator.parameters()), mkdist.FlatGradSync(discriminator.parameters()),
+                              mkdist.FlatGradSync(kp_detector.parameters()))
         self.use_graph, self.warmup = bool(use_graph), warmup
         self.graph = None
         self.static_in = self.static_out = None
         self.kernels_per_step = 0
 
     def _iteration(self, x):
-        g_vals, d_vals = train_iteration(self.g_full, self.d_full, self.optimizers, self.train_params, x)
+        g_vals, d_vals = train_iteration(self.g_full, self.d_full, self.optimizers, self.train_params, x,
+                                         self.grad_sync)
         return torch.stack([v.detach() for v in g_vals + d_vals])
 
     def _snapshot(self):

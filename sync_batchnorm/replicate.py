@@ -15,6 +15,7 @@ from torch import nn
 import torch.distributed as dist
 
 _hooked = set()
+HOOKS_ENABLED = True   # monkey_net_b200.train_step.GraphedTrainer switches to one flat all-reduce per optimiser step
 
 
 def _to_device(obj, device):
@@ -28,6 +29,8 @@ def _to_device(obj, device):
 
 
 def _avg_hook(p):
+    if not HOOKS_ENABLED:
+        return
     w = dist.get_world_size()
     dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
     p.grad.div_(w)

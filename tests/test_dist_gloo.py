@@ -131,6 +131,31 @@ def test_gradsync_buckets():
             assert torch.allclose(g, p.grad, atol=1e-6)
 
 
+def _flat_gradsync(rank, world):
+    from monkey_net_b200 import dist as mkdist
+    torch.manual_seed(4)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
+    sync = mkdist.FlatGradSync(net.parameters())
+    opt = torch.optim.SGD(net.parameters(), lr=0.0)
+    x = mkdist.shard_batch(torch.arange(32.).reshape(8, 4) / 10)
+    net(x).sum(1).mean().backward()
+    opt.zero_grad(set_to_none=False)          # torch-0.4.1-style zeroing keeps the views
+    assert sync.intact() and float(sync.flat.abs().sum()) == 0.0
+    net(x).sum(1).mean().backward()           # autograd accumulates INTO the flat buffer
+    sync.sync()                               # one all-reduce for all parameters
+    return [p.grad.clone() for p in net.parameters()], sync.intact()
+
+
+def test_flat_gradsync_is_one_allreduce_over_views():
+    torch.manual_seed(4)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
+    net(torch.arange(32.).reshape(8, 4) / 10).sum(1).mean().backward()
+    for grads, intact in _spawn(_flat_gradsync):
+        assert intact
+        for g, p in zip(grads, net.parameters()):
+            assert torch.allclose(g, p.grad, atol=1e-6)
+
+
 def test_facade_rejects_single_process_multi_device():
     from sync_batchnorm import DataParallelWithCallback
     with pytest.raises(RuntimeError, match='one-process-per-GPU'):

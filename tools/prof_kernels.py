@@ -17,6 +17,7 @@ def timeit(fn, flush, reps=5):
     st = torch.cuda.current_stream().cuda_stream
     ts = []
     for i in range(reps + 2):
+        lib.call('mk_fill_zero', flush.data_ptr(), flush.numel(), st)
         lib.call('mk_l2_evict', flush.data_ptr(), flush.numel(), st)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); fn(); e.record()

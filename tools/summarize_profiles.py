@@ -10,7 +10,11 @@ import re
 import subprocess
 import sys
 
-KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+KEYS = ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'launch__waves_per_multiprocessor',
+        'sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+        'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_bytes.sum',
+        'l1tex__m_xbar2l1tex_read_bytes.sum', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size',
         'launch__block_size', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
