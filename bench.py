@@ -241,6 +241,10 @@ def run_ours(args):
         from monkey_net_b200 import ops as _ops
         _ops.lib.call = traced
         torch.cuda.synchronize()
+        # The eager loop is CPU-bound at this size (host launch cost > kernel time): an event pair would then
+        # measure the host gap, not the kernel.  Park the stream behind a ~40 ms spin so the host enqueues the whole
+        # iteration ahead of the device; every pair then brackets back-to-back device execution.
+        torch.cuda._sleep(int(0.040 * 1.9e9))
         trainer._iteration(resident)  # eager (ungraphed) pass so every conv launch can be bracketed by events
         torch.cuda.synchronize()
         lib.call = orig
@@ -277,14 +281,18 @@ def run_ours(args):
     out['roofline'] = {'bound': 'tensor', 'kernel': 'k_conv_tc/k_wgrad_tc (tcgen05 tf32) + k_conv_ffma/k_conv_wgrad (fp32) - implicit-GEMM conv fwd, dgrad, wgrad',
                        'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                        'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
+                       'frac_of_tf32_peak': achieved / (pk['bf16_tflops_sustained'] / 2),
+                       'tf32_note': 'kind::tf32 issues at half the bf16 rate: the TF32 ceiling is peak/2; at 64x64 with '
+                                    '16-128 channels the convs are L2->SMEM-bandwidth bound, not tensor bound '
+                                    '(profiles/r1_ncu_conv_tc.md)',
                        'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
                        'launches_per_step': n_conv, 'conv_ms_per_step': conv_ms,
                        'conv_share_of_step': conv_ms / (ms / args.steps),
-                       'note': 'conv kernels timed in an eager pass with CUDA events around every launch; algorithmic '
+                       'note': 'conv kernels timed in an eager pass (stream parked behind a spin so launches are back to back) with CUDA events around every launch; algorithmic '
                                'FLOPs = 3*KP2 + 3*G + 12*D conv FLOPs (2*MACs of the reference convs)'}
-    if not args.no_kernel_bench:
+    if world == 1 and not args.no_kernel_bench:
         out['kernels'] = kernel_bench(device, pk)
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:  # 'on rank 0 at N=1 only'
         out['cpu_baseline'] = cpu_baseline(args, cfg)
     if world == 1 and conv_mode == 'tf32' and not args.no_kernel_bench:
         # the same step with the EXACT fp32 (FFMA) convolutions, for readers who want the no-TF32 number
