@@ -47,6 +47,8 @@ def parse():
                     help="train = configs[1] (the headline); transfer = configs[2]: moving-gif nets, 256x256, "
                          "transfer_one on 16 sources x 2 driving frames (use --config moving-gif --res 256 --batch 16)")
     ap.add_argument('--no-transfer', action='store_true', help='skip the 256x256 transfer side measurement')
+    ap.add_argument('--adam', default='flat', choices=['flat', 'torch'],
+                    help='flat = monkey_net_b200.optim.FlatAdam (one fused launch per optimiser step); torch = torch.optim.Adam')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-bench', action='store_true')
     return ap.parse_args()
@@ -167,7 +169,7 @@ def run_ours(args):
     for m in (gen, disc, kp):
         m.train()
     use_graph = args.graph == 'on' or (args.graph == 'auto')
-    trainer = train_step.GraphedTrainer(kp, gen, disc, tp, use_graph=use_graph)
+    trainer = train_step.GraphedTrainer(kp, gen, disc, tp, use_graph=use_graph, fused_adam=(args.adam == 'flat'))
     B = args.batch
     torch.manual_seed(100 + rank)
     host = {'source': torch.rand(B, 3, 1, args.res, args.res).pin_memory(),
@@ -269,6 +271,7 @@ def run_ours(args):
                                'frame, fwd+bwd+Adam for G, KP and D' % (args.config, B, args.res, args.res),
                    'global_batch': B * world, 'parallelism': 'dp%d' % world,
                    'cuda_graph': trainer.graph is not None, 'conv_mode': conv_mode,
+                   'optimizer': 'FlatAdam (mk_adam_flat, fused zero_grad)' if args.adam == 'flat' else 'torch.optim.Adam',
                    'l2': 'flushed between timed steps: 256 MiB memset (write) followed by a read pass over the same buffer so no dirty lines are left to be written back inside the timed region; both outside the per-step event pairs',
                    'conv_gflop_per_sample': flops['train_step_per_sample'] / 1e9},
         'e2e': {'value': frames / (ms_e2e / 1e3), 'unit': 'frames/s',

@@ -181,6 +181,64 @@ MK_EXPORT int mk_adam_step(float* p, const float* g, float* m, float* v, long lo
     return mk_check_launch("mk_adam_step");
 }
 
+// Whole-group Adam for CUDA graphs: parameters, gradients and both moments of one optimiser live in flat buffers, the
+// step count lives in DEVICE memory (a captured graph replays the same kernel arguments every iteration, so the bias
+// corrections cannot be host scalars), and the gradient is zeroed in the same pass (train.py:118-136 calls
+// optimizer.zero_grad() right after every step).  The last CTA to finish advances the step counter - every CTA has
+// read it by then.  torch.optim.Adam(capturable=True) spends ~450 launches per training iteration on the same work.
+__global__ void __launch_bounds__(256) k_adam_flat(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2,
+                                                   float eps, long long* step, unsigned* ticket, int zero_grad) {
+    const long long t = *reinterpret_cast<volatile long long*>(step) + 1;
+    const float bc1 = (float)(1.0 - pow((double)b1, (double)t));
+    const float bc2 = (float)(1.0 - pow((double)b2, (double)t));
+    const float step_size = lr / bc1;
+    const float rs = 1.f / sqrtf(bc2);
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 gi = ld4(g + i * 4);
+        float4 mi = ld4(m + i * 4), vi = ld4(v + i * 4), pi = ld4(p + i * 4);
+        mi.x = b1 * mi.x + (1.f - b1) * gi.x; mi.y = b1 * mi.y + (1.f - b1) * gi.y;
+        mi.z = b1 * mi.z + (1.f - b1) * gi.z; mi.w = b1 * mi.w + (1.f - b1) * gi.w;
+        vi.x = b2 * vi.x + (1.f - b2) * gi.x * gi.x; vi.y = b2 * vi.y + (1.f - b2) * gi.y * gi.y;
+        vi.z = b2 * vi.z + (1.f - b2) * gi.z * gi.z; vi.w = b2 * vi.w + (1.f - b2) * gi.w * gi.w;
+        pi.x -= step_size * (mi.x / (sqrtf(vi.x) * rs + eps)); pi.y -= step_size * (mi.y / (sqrtf(vi.y) * rs + eps));
+        pi.z -= step_size * (mi.z / (sqrtf(vi.z) * rs + eps)); pi.w -= step_size * (mi.w / (sqrtf(vi.w) * rs + eps));
+        st4(m + i * 4, mi); st4(v + i * 4, vi); st4(p + i * 4, pi);
+        if (zero_grad) st4(g + i * 4, f4zero());
+    }
+    // scalar tail (n not a multiple of 4): handled by the first threads of CTA 0
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = (n4 << 2) + threadIdx.x;
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi, vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        p[i] -= step_size * (mi / (sqrtf(vi) * rs + eps));
+        if (zero_grad) g[i] = 0.f;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {  // last CTA: everyone has read *step
+            *step = t;
+            *ticket = 0u;
+        }
+    }
+}
+
+MK_EXPORT int mk_adam_flat(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                           float eps, long long* step, unsigned* ticket, int zero_grad, void* stream) {
+    if (n <= 0) return 0;
+    MK_REQUIRE(step != nullptr && ticket != nullptr, "mk_adam_flat: step / ticket must be device pointers");
+    long long blocks = mk_cdiv(mk_cdiv(n, 4), 256);
+    const long long cap = (long long)mk_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_adam_flat<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, ticket,
+                                                                   zero_grad);
+    return mk_check_launch("mk_adam_flat");
+}
+
 // ------------------------------------------------------------------------------------------------ sigmoid backward
 __global__ void k_sigmoid_bwd(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dz,
                               long long nv) {

@@ -57,9 +57,14 @@ def make_optimizers(generator, discriminator, kp_detector, lr):
 
 def train_iteration(generator_full_par, discriminator_full_par, optimizers, train_params, x, grad_sync=None):
     """One loop body of train.py:110-136.  Returns (generator loss tensors, discriminator loss tensors).
-    `grad_sync` = (sync_g, sync_d, sync_kp) FlatGradSync objects for data-parallel runs (one all-reduce per optimiser
-    step, gradients zeroed in place like torch 0.4.1 did); None = the reference's code verbatim."""
+    `optimizers` are torch.optim.Adam objects (the reference's code verbatim; with `grad_sync` = (sync_g, sync_d,
+    sync_kp) FlatGradSync objects for data-parallel runs: one all-reduce per optimiser step, gradients zeroed in place
+    like torch 0.4.1 did) or monkey_net_b200.optim.FlatAdam objects (one fused launch per step that also zeroes its
+    gradients and owns the flat all-reduce)."""
+    from .optim import FlatAdam
     opt_g, opt_d, opt_kp = optimizers
+    if isinstance(opt_g, FlatAdam):
+        return _train_iteration_flat(generator_full_par, discriminator_full_par, optimizers, train_params, x)
     keep = grad_sync is not None
     zero = (lambda o: o.zero_grad(set_to_none=False)) if keep else (lambda o: o.zero_grad())
     sync = (lambda i: grad_sync[i].sync()) if keep else (lambda i: None)
@@ -81,6 +86,28 @@ def train_iteration(generator_full_par, discriminator_full_par, optimizers, trai
     return g_vals, loss_values
 
 
+def _train_iteration_flat(generator_full_par, discriminator_full_par, optimizers, train_params, x):
+    """train.py:110-136 with FlatAdam: `step()` = all-reduce (N > 1) + update + zero_grad of that group in one launch."""
+    opt_g, opt_d, opt_kp = optimizers
+    out = generator_full_par(x)
+    loss_values = [val.mean() for val in out[:-2]]
+    generated, kp_joined = out[-2], out[-1]
+    loss = sum(loss_values)
+    loss.backward(retain_graph=not train_params['detach_kp_discriminator'])
+    opt_g.sync_gradients(); opt_g.step()      # optimizer_generator.step(); .zero_grad()
+    opt_d.zero_grad()                         # optimizer_discriminator.zero_grad()
+    if train_params['detach_kp_discriminator']:
+        opt_kp.sync_gradients(); opt_kp.step()
+    g_vals = loss_values
+    loss_values = [val.mean() for val in discriminator_full_par(x, kp_joined, generated)]
+    loss = sum(loss_values)
+    loss.backward()
+    opt_d.sync_gradients(); opt_d.step()
+    if not train_params['detach_kp_discriminator']:
+        opt_kp.sync_gradients(); opt_kp.step()
+    return g_vals, loss_values
+
+
 class GraphedTrainer:
     """The training iteration as ONE CUDA graph launch (B200 design rule: streams and graphs, not a tracing compiler).
 
@@ -92,7 +119,8 @@ class GraphedTrainer:
     in pinned host memory) + one graph replay.  Same arithmetic, same kernels, same update order as train.py:110-136.
     """
 
-    def __init__(self, kp_detector, generator, discriminator, train_params, use_graph=True, warmup=3):
+    def __init__(self, kp_detector, generator, discriminator, train_params, use_graph=True, warmup=3,
+                 fused_adam=True):
         from sync_batchnorm import DataParallelWithCallback
         self.modules = (kp_detector, generator, discriminator)
         self.train_params = train_params
@@ -102,9 +130,6 @@ class GraphedTrainer:
                                                device_ids=ids)
         self.d_full = DataParallelWithCallback(DiscriminatorFullModel(kp_detector, generator, discriminator,
                                                                       train_params), device_ids=ids)
-        mk = lambda m: torch.optim.Adam(m.parameters(), lr=train_params['lr'], betas=(0.5, 0.999),
-                                        capturable=bool(use_graph))
-        self.optimizers = (mk(generator), mk(discriminator), mk(kp_detector))
         self.grad_sync = None
         from . import dist as mkdist
         if mkdist.world() > 1:
@@ -112,8 +137,19 @@ class GraphedTrainer:
             # per-parameter hooks (about 200 latency-bound collectives per iteration)
             import sync_batchnorm.replicate as rep
             rep.HOOKS_ENABLED = False
-            self.grad_sync = (mkdist.FlatGradSync(generator.parameters()), mkdist.FlatGradSync(discriminator.parameters()),
-                              mkdist.FlatGradSync(kp_detector.parameters()))
+        self.fused_adam = bool(fused_adam)
+        if self.fused_adam:
+            from .optim import FlatAdam
+            mk = lambda m: FlatAdam(m.parameters(), lr=train_params['lr'], betas=(0.5, 0.999))
+            self.optimizers = (mk(generator), mk(discriminator), mk(kp_detector))
+        else:
+            mk = lambda m: torch.optim.Adam(m.parameters(), lr=train_params['lr'], betas=(0.5, 0.999),
+                                            capturable=bool(use_graph))
+            self.optimizers = (mk(generator), mk(discriminator), mk(kp_detector))
+            if mkdist.world() > 1:
+                self.grad_sync = (mkdist.FlatGradSync(generator.parameters()),
+                                  mkdist.FlatGradSync(discriminator.parameters()),
+                                  mkdist.FlatGradSync(kp_detector.parameters()))
         self.use_graph, self.warmup = bool(use_graph), warmup
         self.graph = None
         self.static_in = self.static_out = None
@@ -133,6 +169,9 @@ class GraphedTrainer:
         for m, sd in zip(self.modules, snap[0]):
             m.load_state_dict(sd)
         for o, sd in zip(self.optimizers, snap[1]):
+            if self.fused_adam:
+                o.load_state_dict(sd)
+                continue
             if len(sd['state']) == 0:
                 # fresh optimiser: keep the (now allocated) moment / step tensors - the graph must capture only the
                 # update, not their lazy zero-initialisation - and reset their values in place

@@ -61,3 +61,52 @@ def test_pinned_host_batch_path():
     l1 = tr.step(x).cpu()
     l2 = tr.step(x).cpu()
     assert torch.isfinite(l1).all() and torch.isfinite(l2).all() and not torch.equal(l1, l2)
+
+
+def test_flat_adam_equals_torch_adam():
+    """monkey_net_b200.optim.FlatAdam (one mk_adam_flat launch per group, device-side step count, fused zero_grad) ==
+    torch.optim.Adam(lr, betas=(0.5, 0.999)) of train.py:81-83, step by step, on ragged parameter shapes."""
+    from monkey_net_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    shapes = [(7,), (3, 5), (16, 4, 1, 3, 3), (1,), (130,)]
+    pa = [torch.nn.Parameter(torch.randn(*s, device='cuda')) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    opt_a = FlatAdam(pa, lr=2e-4, betas=(0.5, 0.999))
+    opt_b = torch.optim.Adam(pb, lr=2e-4, betas=(0.5, 0.999))
+    assert opt_a.intact()
+    for step in range(4):
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(b) * (10.0 ** (step - 2))
+            a.grad.add_(g)               # accumulate INTO the flat view, as autograd does
+            b.grad = g.clone()
+        opt_a.step()
+        opt_b.step()
+        assert opt_a.intact() and int(opt_a.step_count) == step + 1
+        for a, b in zip(pa, pb):
+            assert float(a.grad.abs().max()) == 0.0          # zeroed by the same launch
+            assert helpers.max_abs(a, b) < 2e-7 + 1e-6 * float(b.abs().max()), step
+    sd = opt_a.state_dict()
+    opt_a.step()
+    opt_a.load_state_dict(sd)
+    assert int(opt_a.step_count) == 4
+
+
+def test_graphed_trainer_flat_adam_matches_torch_adam_first_step():
+    """The fused optimiser path of GraphedTrainer against the torch.optim.Adam path: same losses, same first update."""
+    from monkey_net_b200 import train_step
+    cfg = helpers.tiny_config()
+    tp = cfg['train_params']
+    x = {'source': helpers.smooth_frames(4, 1, 32, 10).cuda(), 'video': helpers.smooth_frames(4, 1, 32, 20).cuda()}
+    ga, da, ka = _nets(cfg)
+    gb, db, kb = _nets(cfg)
+    ta = train_step.GraphedTrainer(ka, ga, da, tp, use_graph=True, fused_adam=True)
+    tb = train_step.GraphedTrainer(kb, gb, db, tp, use_graph=False, fused_adam=False)
+    la, lb = ta.step(x).clone(), tb.step(x).clone()
+    assert helpers.max_abs(la, lb) < 2e-5 * max(1.0, float(lb.abs().max())), (la, lb)
+    tot = flips = 0
+    for (n1, p1), (n2, p2) in zip(ga.named_parameters(), gb.named_parameters()):
+        if helpers.structurally_zero_grad(n1):
+            continue
+        diff = (p1.detach() - p2.detach()).abs()
+        tot += diff.numel(); flips += int((diff > 0.5 * tp['lr']).sum())
+    assert flips / tot < 1e-3, (flips, tot)
