@@ -158,8 +158,9 @@ def run_ours(args):
     device = torch.device('cuda', local)
     if world > 1:
         import datetime
-        # a rank that dies or diverges must fail the run in minutes, not hang the box for NCCL's default 10
-        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=180))
+        # rendezvous of 8 cold-starting ranks can take minutes on a fresh box (first `import torch`); collectives
+        # themselves are milliseconds, so a diverged rank still fails the run well inside the driver's patience
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=480))
     lib.load()
     from monkey_net_b200 import ops as mkops
     conv_mode = mkops.CONV_MODE
@@ -580,7 +581,7 @@ def run_transfer(args):
     device = torch.device('cuda', local)
     if world > 1:
         import datetime
-        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=480))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

@@ -192,6 +192,33 @@ def test_batched_transfer_equals_reference_loop(name):
     assert helpers.max_abs(g1, a['video_prediction']) < 1e-5 and helpers.max_abs(g2, g1) < 1e-6
 
 
+def test_non_square_frames_and_single_sample():
+    """The nets are fully convolutional: 32x64 frames (H != W), batch 1, two driving frames, eval mode."""
+    from oracle import monkey_oracle as mo
+    cfg = helpers.tiny_config()
+    gen, disc, kp = build_product(cfg)
+    og, od, ok = mo.build_from_config(cfg)
+    og.load_state_dict(gen.state_dict()); ok.load_state_dict(kp.state_dict())
+    for m in (gen, kp):
+        m.cuda().eval()
+    for m in (og, ok):
+        m.eval()
+    torch.manual_seed(3)
+    wide = helpers.smooth_frames(1, 3, 64, 7)[:, :, :, 16:48, :]          # (1,3,3,32,64), a NON-contiguous crop
+    src, drv = wide[:, :, :1], wide[:, :, 1:]
+    with torch.no_grad():
+        b = ok(drv)
+        a = kp(drv.cuda())
+        assert helpers.max_abs(a['mean'], b['mean']) < 2e-5 and helpers.max_abs(a['var'], b['var']) < 2e-5
+        ks = ok(src)
+        ref = og(src, kp_driving=b, kp_source=ks)
+        out = gen(src.cuda(), kp_driving={k: v.cuda() for k, v in b.items()},
+                  kp_source={k: v.cuda() for k, v in ks.items()})
+    assert out['video_prediction'].shape == ref['video_prediction'].shape == (1, 3, 2, 32, 64)
+    assert helpers.max_abs(out['video_prediction'], ref['video_prediction']) < 1e-3
+    assert helpers.max_abs(out['video_deformed'], ref['video_deformed']) < 1e-4
+
+
 def test_cpu_tensor_is_rejected_loudly():
     cfg = helpers.tiny_config()
     gen, disc, kp = build_product(cfg)
