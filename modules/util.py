@@ -110,8 +110,7 @@ class UpBlock3D(_Block):
         _spatial(kernel_size)
 
     def run(self, a, extras=()):
-        y = ops.conv(a, self.conv.weight, self.conv.bias, pad=self.pad, ups=True)
-        return ops.norm_act(y, self.norm, mode='bn', slope=0.0, extras=extras)
+        return ops.conv_bn_relu(a, self.conv, self.norm, self.pad, ups=True, extras=extras)
 
 
 class DownBlock3D(_Block):
@@ -125,8 +124,7 @@ class DownBlock3D(_Block):
         _spatial(kernel_size)
 
     def run(self, a):
-        y = ops.conv(a, self.conv.weight, self.conv.bias, pad=self.pad)
-        return ops.norm_act(y, self.norm, mode='bn', slope=0.0, pool=1)
+        return ops.conv_bn_relu(a, self.conv, self.norm, self.pad, pool=1)
 
 
 class SameBlock3D(_Block):
@@ -140,8 +138,7 @@ class SameBlock3D(_Block):
         _spatial(kernel_size)
 
     def run(self, a):
-        y = ops.conv(a, self.conv.weight, self.conv.bias, pad=self.pad, groups=self.groups)
-        return ops.norm_act(y, self.norm, mode='bn', slope=0.0)
+        return ops.conv_bn_relu(a, self.conv, self.norm, self.pad, groups=self.groups)
 
 
 class Encoder(nn.Module):

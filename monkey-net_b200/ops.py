@@ -294,10 +294,126 @@ class _Conv(torch.autograd.Function):
 
 def conv(a, weight, bias, pad, groups=1, ups=False, resid=None, act=None, pool=0):
     """nn.Conv3d (1,k,k) as a per-frame 2-D conv; returns a single-segment Act."""
+    if INFER_FUSION and not torch.is_grad_enabled():
+        return conv_infer(a, weight, bias, pad, groups=groups, ups=ups, resid=resid,
+                          act={None: 0, 'relu': 1, 'sigmoid': 2}[act], pool=pool)
     y = _Conv.apply(a.t, weight, bias, resid.t if resid is not None else None, a.segs, pad, groups, int(ups), act,
                     pool)
     co = weight.shape[0]
     return Act(y, ((co, pad4(co)),))
+
+
+# ---------------------------------------------------------------------------------------------- inference fast path
+# Under torch.no_grad() (transfer.py / reconstruction.py run the nets in eval mode without autograd) nothing has to
+# be saved for backward and the parameters do not change between calls:
+#   * the packed GEMM weights and the epilogue vectors are CACHED per parameter version instead of re-packed by a
+#     kernel on every call;
+#   * conv -> eval-BatchNorm -> ReLU is ONE launch: the BN of running statistics folds into the conv epilogue,
+#     scale = gamma * invstd, shift = beta + (bias - running_mean) * scale (batchnorm.py:50-53 with training=False),
+#     which removes a full read + write pass per block.
+# The tensor-core kernel splits K only for a linear epilogue, so layers whose tile count cannot fill the machine
+# (deep 2x2 ... 8x8 levels) keep conv (split-K) + norm_apply.
+INFER_FUSION = os.environ.get('MONKEY_B200_INFER_FUSION', '1') != '0'
+_INFER_CACHE = {}
+# Kernels update parameters and BN running statistics through raw pointers (mk_norm_finalize, mk_adam_flat, CUDA-graph
+# replays of a training step), which torch's per-tensor version counters do not see: every such update bumps this
+# epoch and thereby invalidates the cached packs.
+_PARAM_EPOCH = [0]
+
+
+def note_parameters_changed():
+    _PARAM_EPOCH[0] += 1
+
+
+def _versions(*ts):
+    return (_PARAM_EPOCH[0],) + tuple((t.data_ptr(), t._version) if t is not None else None for t in ts)
+
+
+def _infer_pack(weight, bias, segs, groups, ups, norm, Cp, tc):
+    """(packed weights, scale or None, shift or None) for this conv (+ folded eval BN), cached on parameter versions."""
+    import weakref
+    key = (id(weight), segs, int(ups), bool(tc), id(norm) if norm is not None else None)
+    nt = (norm.weight, norm.bias, norm.running_mean, norm.running_var) if norm is not None else ()
+    ver = _versions(weight, bias, *nt)
+    hit = _INFER_CACHE.get(key)
+    if hit is not None and hit[0] == ver and hit[1]() is weight:
+        return hit[2]
+    Co, Cig, _, R, S = weight.shape
+    Cop = pad4(Co)
+    st = _stream()
+    cmap, _ = _channel_maps(segs, weight.device)
+    wpack = _empty((16 if (tc and ups) else R * S) * Cp * Cop, like=weight)
+    bias_p = _empty(Cop, like=weight) if bias is not None else None
+    lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop,
+             (4 if ups else 2) if tc else 0, wpack.data_ptr(), _ptr(bias), _ptr(bias_p), st)
+    scale = None
+    shift = bias_p
+    if norm is not None:
+        with torch.no_grad():
+            sc = norm.weight.detach() * torch.rsqrt(norm.running_var.detach().double() + 1e-5).float()
+            b0 = bias.detach() if bias is not None else torch.zeros_like(sc)
+            sh = norm.bias.detach() + (b0 - norm.running_mean.detach()) * sc
+            scale = torch.zeros(Cop, dtype=torch.float32, device=weight.device)
+            shift = torch.zeros(Cop, dtype=torch.float32, device=weight.device)
+            scale[:Co] = sc
+            shift[:Co] = sh
+    val = (wpack, scale, shift)
+    _INFER_CACHE[key] = (ver, weakref.ref(weight), val)
+    return val
+
+
+def _tc_would_split(npix, cop, niter):
+    """mirror of mk_conv2d_tc's split-K decision (conv_tc.cu): few tiles and a linear epilogue"""
+    tiles = ((npix + 127) // 128) * ((cop + 127) // 128)
+    return tiles * 2 <= 148 and niter >= 4
+
+
+def conv_infer(a, weight, bias, pad, groups=1, ups=False, resid=None, act=0, slope=0.0, pool=0, norm=None):
+    """Inference-only convolution (no autograd): y = pool(act((conv(x) + bias) [folded eval-BN of `norm`] + resid))."""
+    x = a.t
+    _check(x, 'conv input')
+    N, Hin, Win, Cp = x.shape
+    Co, Cig, _, R, S = weight.shape
+    Cop = pad4(Co)
+    ups = int(bool(ups))
+    tc = _tc_ok(Cp, Cop, ups, 0, R, groups)
+    wpack, scale, shift = _infer_pack(weight, bias, a.segs, groups, ups, norm, Cp, tc)
+    Hl, Wl = Hin << ups, Win << ups
+    Ho, Wo = Hl + 2 * pad - R + 1, Wl + 2 * pad - S + 1
+    st = _stream()
+    rp, ldr = (resid.t.data_ptr(), Cop) if resid is not None else (None, 0)
+    if tc:
+        y = _empty(N, Ho, Wo, Cop, like=x)
+        lib.call('mk_conv2d_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, _ptr(scale),
+                 _ptr(shift), rp, ldr, act, float(slope), y.data_ptr(), Cop, Cop, st)
+        out = Act(y, ((Co, Cop),))
+        if pool:
+            out = norm_act(out, None, mode='none', pool=1)
+        return out
+    y = _empty(N, Ho >> 1, Wo >> 1, Cop, like=x) if pool else _empty(N, Ho, Wo, Cop, like=x)
+    lib.call('mk_conv2d', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, _ptr(scale), _ptr(shift),
+             rp, ldr, act, float(slope), y.data_ptr(), Cop, Cop, int(pool), st)
+    return Act(y, ((Co, Cop),))
+
+
+def conv_bn_relu(a, conv_mod, norm_mod, pad, groups=1, ups=False, pool=0, extras=()):
+    """conv -> BatchNorm -> ReLU [-> 2x2 average pool] [-> concat(extras)]: the body of DownBlock3D / UpBlock3D /
+    SameBlock3D (util.py:91-126).  Training or autograd: conv + the two-phase norm kernels.  Inference (eval-mode BN,
+    no autograd): one fused conv launch where the layer has enough tiles, see above."""
+    infer = INFER_FUSION and not torch.is_grad_enabled() and not norm_mod.training
+    if infer:
+        N, Hin, Win, Cp = a.t.shape
+        Co, _, _, R, S = conv_mod.weight.shape
+        u = int(bool(ups))
+        npix = N * Hin * Win if u else N * ((Hin + 2 * pad - R + 1) * (Win + 2 * pad - S + 1))
+        niter = (4 if u else R * S) * ((Cp + 31) // 32)
+        tc = _tc_ok(Cp, pad4(Co), u, 0, R, groups)
+        if not (tc and _tc_would_split(npix, pad4(Co), niter)):
+            y = conv_infer(a, conv_mod.weight, conv_mod.bias, pad, groups=groups, ups=ups, act=1, slope=0.0,
+                           pool=pool, norm=norm_mod)
+            return norm_act(y, None, mode='none', extras=extras) if extras else y
+    y = conv(a, conv_mod.weight, conv_mod.bias, pad=pad, groups=groups, ups=ups)
+    return norm_act(y, norm_mod, mode='bn', slope=0.0, pool=pool, extras=extras)
 
 
 # ====================================================================================================== norm + act
@@ -321,6 +437,7 @@ class _NormAct(torch.autograd.Function):
             lib.call('mk_norm_finalize', sums.data_ptr(), 1, C, Cp, count, _ptr(gamma), _ptr(beta), 1e-5,
                      module.running_mean.data_ptr(), module.running_var.data_ptr(), 0.1,
                      module.num_batches_tracked.data_ptr(), params.data_ptr(), st)
+            note_parameters_changed()  # running statistics written through raw pointers
         elif mode == 'bn':
             params = _empty(4 * Cp, like=x)
             lib.call('mk_norm_eval_params', module.running_mean.data_ptr(), module.running_var.data_ptr(), _ptr(gamma),

@@ -63,6 +63,8 @@ class FlatAdam:
                  self.exp_avg_sq.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1], self.eps,
                  self.step_count.data_ptr(), self._ticket.data_ptr(), 1 if zero_grad else 0,
                  torch.cuda.current_stream().cuda_stream)
+        from . import ops
+        ops.note_parameters_changed()  # in-place update through raw pointers: invalidate cached inference packs
 
     def zero_grad(self, set_to_none=False):
         if set_to_none:

@@ -213,4 +213,6 @@ class GraphedTrainer:
         for k, v in x.items():
             self.static_in[k].copy_(v, non_blocking=True)
         self.graph.replay()
+        from . import ops
+        ops.note_parameters_changed()  # the replay updated parameters and running statistics without any Python
         return self.static_out

@@ -219,6 +219,55 @@ def test_non_square_frames_and_single_sample():
     assert helpers.max_abs(out['video_deformed'], ref['video_deformed']) < 1e-4
 
 
+@pytest.mark.parametrize('mode', ['fp32', 'tf32'])
+def test_inference_fusion_equals_unfused_and_cache_invalidation(mode):
+    """no_grad + eval: conv + folded eval-BN + ReLU in one launch with cached weight packs == the unfused kernels;
+    the cache must notice parameter / running-statistics updates done through raw pointers (a training-mode forward
+    and an optimiser step in between)."""
+    from monkey_net_b200 import ops
+    from monkey_net_b200.optim import FlatAdam
+    cfg = helpers.load_config('shapes')
+    gen, disc, kp = build_product(cfg)
+    for m in (gen, kp):
+        m.cuda()
+    x = {k: v.cuda() for k, v in {'source': helpers.smooth_frames(2, 1, 64, 5), 'video': helpers.smooth_frames(2, 2, 64, 6)}.items()}
+    prev_mode, prev_fusion = ops.CONV_MODE, ops.INFER_FUSION
+    ops.set_conv_mode(mode)
+    tol = 2e-6 if mode == 'fp32' else 2e-5
+
+    def evaluate(fusion):
+        ops.INFER_FUSION = fusion
+        for m in (gen, kp):
+            m.eval()
+        with torch.no_grad():
+            k = kp(x['video'])
+            ks = kp(x['source'])
+            return k['mean'].clone(), gen(x['source'], kp_driving=k, kp_source=ks)['video_prediction'].clone()
+
+    try:
+        k1, p1 = evaluate(True)
+        k1b, p1b = evaluate(True)            # second call: served from the cache
+        k0, p0 = evaluate(False)
+        assert helpers.max_abs(k1, k0) < tol and helpers.max_abs(p1, p0) < tol
+        assert helpers.max_abs(p1b, p1) == 0.0
+        # change running statistics (train-mode forward) and parameters (one optimiser step) through the kernels
+        ops.INFER_FUSION = True
+        for m in (gen, kp):
+            m.train()
+        opt = FlatAdam(list(gen.parameters()) + list(kp.parameters()), lr=1e-2, betas=(0.5, 0.999))
+        kj = kp(torch.cat([x['source'], x['video'][:, :, :1]], 2))
+        out = gen(x['source'], {k: v[:, 1:] for k, v in kj.items()}, {k: v[:, :1] for k, v in kj.items()})
+        out['video_prediction'].mean().backward()
+        opt.step()
+        k2, p2 = evaluate(True)
+        k3, p3 = evaluate(False)
+        assert helpers.max_abs(p2, p1) > 1e-4, 'the update did not change the output: test is vacuous'
+        assert helpers.max_abs(k2, k3) < tol and helpers.max_abs(p2, p3) < tol
+    finally:
+        ops.set_conv_mode(prev_mode)
+        ops.INFER_FUSION = prev_fusion
+
+
 def test_cpu_tensor_is_rejected_loudly():
     cfg = helpers.tiny_config()
     gen, disc, kp = build_product(cfg)
