@@ -233,7 +233,9 @@ def test_inference_fusion_equals_unfused_and_cache_invalidation(mode):
     x = {k: v.cuda() for k, v in {'source': helpers.smooth_frames(2, 1, 64, 5), 'video': helpers.smooth_frames(2, 2, 64, 6)}.items()}
     prev_mode, prev_fusion = ops.CONV_MODE, ops.INFER_FUSION
     ops.set_conv_mode(mode)
-    tol = 2e-6 if mode == 'fp32' else 2e-5
+    # fused and unfused epilogues round differently (1 ulp); in TF32 mode a 1-ulp difference can cross a TF32
+    # truncation boundary of the next conv's operand, hence the wider bar there
+    tol = 1e-5 if mode == 'fp32' else 2e-4
 
     def evaluate(fusion):
         ops.INFER_FUSION = fusion
