@@ -251,7 +251,8 @@ def test_inference_fusion_equals_unfused_and_cache_invalidation(mode):
         k1b, p1b = evaluate(True)            # second call: served from the cache
         k0, p0 = evaluate(False)
         assert helpers.max_abs(k1, k0) < tol and helpers.max_abs(p1, p0) < tol
-        assert helpers.max_abs(p1b, p1) == 0.0
+        # a cache hit runs the same kernels; split-K combines with fp32 atomics, so repeats agree to rounding only
+        assert helpers.max_abs(p1b, p1) < tol
         # change running statistics (train-mode forward) and parameters (one optimiser step) through the kernels
         ops.INFER_FUSION = True
         for m in (gen, kp):
