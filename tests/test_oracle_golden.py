@@ -49,7 +49,8 @@ def test_synthetic_inputs_are_reproducible():
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason='/root/reference only exists in the build container')
-@pytest.mark.parametrize('name,res', [('moving-gif', 64), ('vox-full', 128), ('bair', 64)])
+@pytest.mark.parametrize('name,res', [('moving-gif', 64), ('vox-full', 128), ('bair', 64), ('taichi', 64), ('shapes', 64),
+                                      ('nemo', 64), ('vox', 128), ('actions', 64)])
 def test_oracle_matches_live_reference(name, res):
     """Forward parity with identical keypoints fed to both (the chain is ill-conditioned w.r.t. 1e-7 kp noise)."""
     cfg = helpers.load_config(name)
