@@ -90,6 +90,13 @@ int mk_conv2d(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int u
 int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups, const float* wpack_tc, int R,
                  int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act, float slope,
                  float* y, int Cout_p, int ldy, void* stream);
+/* EXPERIMENTAL, opt-in (MONKEY_B200_CONV_HALO=1), not yet validated on hardware: same contract as mk_conv2d_tc for
+ * stride-1 3x3 / 4x4 convolutions without upsample on maps of at least 8 x (16-(S-1)) pixels, but the tile's halo is
+ * staged ONCE per channel chunk and every tap reads it as a row-shifted window (csrc/conv_tc_halo.cu).  Returns -2
+ * outside that envelope. */
+int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc, int R, int S,
+                      int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
+                      float slope, float* y, int Cout_p, int ldy, void* stream);
 /* dwpack[R*S][Cin_p][Cout_p] = sum over pixels of im2col(x)^T dy  (zero-filled inside). */
 int mk_conv2d_wgrad(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
                     const float* dy, int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream);

@@ -55,6 +55,30 @@ _MAP_CACHE = {}
 CONV_MODE = os.environ.get('MONKEY_B200_CONV', 'tf32')
 
 
+# EXPERIMENTAL halo-window tensor-core conv (csrc/conv_tc_halo.cu): opt-in, not validated on hardware yet
+CONV_HALO = os.environ.get('MONKEY_B200_CONV_HALO', '0') == '1'
+
+
+def _halo_ok(N, Hin, Win, R, S, pad, ups, groups, cop):
+    if not CONV_HALO or ups or R != S or R not in (3, 4):
+        return False
+    Ho, Wo = Hin + 2 * pad - R + 1, Win + 2 * pad - S + 1
+    twv = 16 - (S - 1)
+    if Ho < 8 or Wo < twv:
+        return False
+    tiles = N * ((Ho + 7) // 8) * ((Wo + twv - 1) // twv) * ((cop + 127) // 128)
+    return tiles >= 148  # the many-tile, L2-bound layers; the few-tile ones keep split-K
+
+
+def _conv_tc_call(x, N, Hin, Win, Cp, ups, wpack, R, S, pad, scale, shift, resid_ptr, ldr, act, slope, y, Cop, groups, st):
+    if _halo_ok(N, Hin, Win, R, S, pad, ups, groups, Cop):
+        lib.call('mk_conv2d_tc_halo', x.data_ptr(), N, Hin, Win, Cp, Cp, wpack.data_ptr(), R, S, pad, scale, shift,
+                 resid_ptr, ldr, act, slope, y.data_ptr(), Cop, Cop, st)
+    else:
+        lib.call('mk_conv2d_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, scale, shift,
+                 resid_ptr, ldr, act, slope, y.data_ptr(), Cop, Cop, st)
+
+
 def set_conv_mode(mode):
     global CONV_MODE
     assert mode in ('fp32', 'tf32')
@@ -220,9 +244,8 @@ class _Conv(torch.autograd.Function):
             y = _empty(N, Ho, Wo, Cop, like=x)
         act_code = {None: 0, 'relu': 1, 'sigmoid': 2}[act]
         if tc:
-            lib.call('mk_conv2d_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, None,
-                     _ptr(bias_p), _ptr(resid), Cop if resid is not None else 0, act_code, 0.0, y.data_ptr(), Cop, Cop,
-                     st)
+            _conv_tc_call(x, N, Hin, Win, Cp, ups, wpack, R, S, pad, None, _ptr(bias_p), _ptr(resid),
+                          Cop if resid is not None else 0, act_code, 0.0, y, Cop, groups, st)
         else:
             lib.call('mk_conv2d', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, None,
                      _ptr(bias_p), _ptr(resid), Cop if resid is not None else 0, act_code, 0.0, y.data_ptr(), Cop, Cop,
@@ -384,8 +407,8 @@ def conv_infer(a, weight, bias, pad, groups=1, ups=False, resid=None, act=0, slo
     rp, ldr = (resid.t.data_ptr(), Cop) if resid is not None else (None, 0)
     if tc:
         y = _empty(N, Ho, Wo, Cop, like=x)
-        lib.call('mk_conv2d_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, _ptr(scale),
-                 _ptr(shift), rp, ldr, act, float(slope), y.data_ptr(), Cop, Cop, st)
+        _conv_tc_call(x, N, Hin, Win, Cp, ups, wpack, R, S, pad, _ptr(scale), _ptr(shift), rp, ldr, act, float(slope),
+                      y, Cop, groups, st)
         out = Act(y, ((Co, Cop),))
         if pool:
             out = norm_act(out, None, mode='none', pool=1)
