@@ -1,5 +1,9 @@
-// EXPERIMENTAL (written at the end of round 1, NOT yet validated on hardware; opt-in through MONKEY_B200_CONV_HALO=1,
-// never on the default path, its GPU test is skipped unless that variable is set).
+// EXPERIMENTAL (written at the end of round 1; opt-in through MONKEY_B200_CONV_HALO=1, never on the default path, its
+// GPU test is skipped unless that variable is set).  STATUS after its only GPU run (the round's last 20 seconds of
+// budget): the kernel runs to completion and writes every output, but the values are wrong (relative error 0.8 on all
+// six test shapes) - consistent with 6 of the 9 windows (those whose row shift 16*r + s is not a multiple of 8)
+// being read with the wrong swizzle phase.  First thing to try next round: MONKEY_B200_HALO_BASEOFF=0 (descriptor
+// base offset left at zero, i.e. the hardware derives the swizzle phase from the absolute address bits).
 //
 // Halo-window tensor-core convolution for sm_100a.  k_conv_tc (conv_tc.cu) fetches the shifted 128-pixel A tile once
 // PER FILTER TAP: ncu on 48->48 3x3 @256x256 shows 1.66 GB crossing L2->SM for a 100 MB input, lts throughput 59 %,
@@ -22,6 +26,7 @@
 #include "common.cuh"
 #include "../../include/monkey_b200.h"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 using namespace mk_tc;
@@ -34,15 +39,16 @@ struct HaloP {
     int N, Ho, Wo, Cout_p, ldy, Cin_p, R, S, pad;
     int TWv, tilesW, tilesH;
     int halo_rows, a_slot, b_slot, a_slots, b_slots, tmem_cols;
+    int use_base_offset;  // 1: descriptor base offset = (start >> 7) & 7 for the shifted windows; 0: leave it zero
     const float* scale; const float* shift; const float* resid; int ldr, act; float slope;
     float* y;
 };
 
 // K-major SWIZZLE_128B operand whose first row is NOT on a 1024-byte atom boundary: base offset = row phase
-__device__ __forceinline__ uint64_t umma_desc_window(const void* smem) {
+__device__ __forceinline__ uint64_t umma_desc_window(const void* smem, int use_base_offset) {
     const uint32_t addr = smem_u32(smem);
     uint64_t d = umma_desc(smem);
-    d |= (uint64_t)((addr >> 7) & 7u) << 49;
+    if (use_base_offset) d |= (uint64_t)((addr >> 7) & 7u) << 49;
     return d;
 }
 
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(256) k_conv_tc_halo(const __grid_constant__ CU
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const int r = tap / p.S, s = tap - r * p.S;
-                    const uint64_t adesc = umma_desc_window(a_ring + as * p.a_slot + (16 * r + s) * 128);
+                    const uint64_t adesc = umma_desc_window(a_ring + as * p.a_slot + (16 * r + s) * 128, p.use_base_offset);
                     const uint64_t bdesc = umma_desc(b_ring + bs * p.b_slot);
                     for (int k = 0; k < nk; ++k)
                         umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | tap | k) ? 1u : 0u);
@@ -202,6 +208,10 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     p.b_slot = b_rows * 128;
     p.tmem_cols = b_rows <= 32 ? 32 : (b_rows <= 64 ? 64 : 128);
     p.scale = scale; p.shift = shift; p.resid = resid; p.ldr = ldr; p.act = act; p.slope = slope; p.y = y;
+    {
+        const char* e = getenv("MONKEY_B200_HALO_BASEOFF");
+        p.use_base_offset = (e && e[0] == '0') ? 0 : 1;
+    }
     const int nchunks = (Cin_p + HK - 1) / HK;
     p.a_slots = nchunks < 2 ? 1 : 2;
     int budget = 100 * 1024 - p.a_slots * p.a_slot;         // two CTAs per SM

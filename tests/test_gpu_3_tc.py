@@ -212,10 +212,10 @@ HALO_CASES = [
 
 
 @pytest.mark.skipif(os.environ.get('MONKEY_B200_CONV_HALO', '0') != '1',
-                    reason='experimental halo-window conv (csrc/conv_tc_halo.cu): written at the end of round 1 without GPU '
-                           'time left to validate it; set MONKEY_B200_CONV_HALO=1 to run.  If it fails only on windows with '
-                           'r or s != 0, the open question is the UMMA descriptor base-offset convention for a start address '
-                           'that is not on a 1024-byte swizzle-atom boundary (umma_desc_window).')
+                    reason='experimental halo-window conv (csrc/conv_tc_halo.cu), opt-in with MONKEY_B200_CONV_HALO=1.  Round-1 status: '
+                           'runs to completion, outputs wrong (rel. error 0.8) - try MONKEY_B200_HALO_BASEOFF=0 first: the open '
+                           'question is the UMMA descriptor base-offset convention for a window that does not start on a '
+                           '1024-byte swizzle-atom boundary (umma_desc_window).')
 @pytest.mark.parametrize('cin,cout,k,pad,H,W,N,resid,act', HALO_CASES)
 def test_conv_tc_halo_matches_fp32_kernel(cin, cout, k, pad, H, W, N, resid, act):
     from monkey_net_b200 import lib
