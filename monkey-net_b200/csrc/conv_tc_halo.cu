@@ -2,8 +2,12 @@
 // GPU test is skipped unless that variable is set).  STATUS after its only GPU run (the round's last 20 seconds of
 // budget): the kernel runs to completion and writes every output, but the values are wrong (relative error 0.8 on all
 // six test shapes) - consistent with 6 of the 9 windows (those whose row shift 16*r + s is not a multiple of 8)
-// being read with the wrong swizzle phase.  First thing to try next round: MONKEY_B200_HALO_BASEOFF=0 (descriptor
-// base offset left at zero, i.e. the hardware derives the swizzle phase from the absolute address bits).
+// being read with the wrong swizzle phase.  That run set the descriptor base offset to (start >> 7) & 7.  Reasoning
+// afterwards: the in-atom K advance every tcgen05 kernel here uses (start address + 32 B per K step, base offset 0)
+// only works if the hardware XORs the 16-byte-chunk bits with the row bits of the FINAL ABSOLUTE shared-memory
+// address - and then a row-shifted window of a 1024-byte-aligned buffer needs NO base offset either; adding one
+// double-counts the phase.  The default is therefore now base offset 0 (MONKEY_B200_HALO_BASEOFF=1 restores the
+// first variant); untested - the round's GPU budget was spent.
 //
 // Halo-window tensor-core convolution for sm_100a.  k_conv_tc (conv_tc.cu) fetches the shifted 128-pixel A tile once
 // PER FILTER TAP: ncu on 48->48 3x3 @256x256 shows 1.66 GB crossing L2->SM for a 100 MB input, lts throughput 59 %,
@@ -16,9 +20,8 @@
 //     16 pixels per image row, 128B-swizzled (out-of-bounds = zero fill = conv padding).  Pixel (row + r, col + s)
 //     of the halo is shared-memory row m + 16*r + s, so tap (r, s) is the same buffer read through a UMMA
 //     descriptor whose start address is advanced by (16*r + s) * 128 B;  the window then no longer starts on a
-//     1024-byte swizzle-atom boundary, which the descriptor's base-offset field (bits 49-51) =
-//     (start address >> 7) & 7 accounts for (PTX ISA, matrix-descriptor "base offset");  the extra halo row covers
-//     the overrun of the last window (m = 127, r = R-1, s = S-1);
+//     1024-byte swizzle-atom boundary (see the status note above for the base-offset question);  the extra halo row
+//     covers the overrun of the last window (m = 127, r = R-1, s = S-1);
 //   * L2->SM bytes per tile and chunk: (8 + R) * 2 KB instead of R*S * 16 KB (6.5x less for 3x3);
 //   * two rings as in wgrad_tc.cu: halo ring (per chunk) and weight ring (per chunk x tap), MMA order chunk-major.
 // Envelope: stride-1, no upsample, R == S in {3, 4}, Ho >= 8, Wo >= TWv, linear or fused epilogue as k_conv_tc,
@@ -210,7 +213,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     p.scale = scale; p.shift = shift; p.resid = resid; p.ldr = ldr; p.act = act; p.slope = slope; p.y = y;
     {
         const char* e = getenv("MONKEY_B200_HALO_BASEOFF");
-        p.use_base_offset = (e && e[0] == '0') ? 0 : 1;
+        p.use_base_offset = (e && e[0] == '1') ? 1 : 0;
     }
     const int nchunks = (Cin_p + HK - 1) / HK;
     p.a_slots = nchunks < 2 ? 1 : 2;

@@ -213,9 +213,9 @@ HALO_CASES = [
 
 @pytest.mark.skipif(os.environ.get('MONKEY_B200_CONV_HALO', '0') != '1',
                     reason='experimental halo-window conv (csrc/conv_tc_halo.cu), opt-in with MONKEY_B200_CONV_HALO=1.  Round-1 status: '
-                           'runs to completion, outputs wrong (rel. error 0.8) - try MONKEY_B200_HALO_BASEOFF=0 first: the open '
-                           'question is the UMMA descriptor base-offset convention for a window that does not start on a '
-                           '1024-byte swizzle-atom boundary (umma_desc_window).')
+                           'with descriptor base offset = (start >> 7) & 7 it ran to completion with wrong outputs (rel. error 0.8); '
+                           'the default is now base offset 0 (absolute-address swizzle, see the file header), untested; '
+                           'MONKEY_B200_HALO_BASEOFF=1 restores the first variant.')
 @pytest.mark.parametrize('cin,cout,k,pad,H,W,N,resid,act', HALO_CASES)
 def test_conv_tc_halo_matches_fp32_kernel(cin, cout, k, pad, H, W, N, resid, act):
     from monkey_net_b200 import lib
