@@ -19,7 +19,9 @@ def nearest_src(dst, n_in, n_out):
 def linear_src(dst, n_in, n_out):
     """common.cuh:linear_src - align_corners=False source index and weight of the upper neighbour"""
     scale = f32(n_in) / f32(n_out)
-    s = scale * (dst.astype(f32) + f32(0.5)) - f32(0.5)
+    # scale * (dst + 0.5) - 0.5 is ONE fused multiply-add on the device (nvcc contracts it, as it does in ATen's
+    # kernel): a single rounding, emulated here through float64
+    s = (np.float64(scale) * np.float64(dst.astype(f32) + f32(0.5)) - 0.5).astype(f32)
     s = np.maximum(s, f32(0))
     i0 = np.minimum(s.astype(np.int64), n_in - 1)
     i1 = i0 + (i0 < n_in - 1)
