@@ -3,6 +3,7 @@ reference driver (it needs imageio / skimage / matplotlib) can run the exact inf
 
   normalize_kp    == transfer.py:31-62  (move_location, movement_mult, clip_mean, adapt_variance)
   transfer_one    == transfer.py:65-79  (KP detector on every driving frame, generator on every frame)
+  reconstruct     == reconstruction.py:12-25,57-62 (frame 0 is the appearance, every frame drives)
 
 Differences, both result-preserving in eval mode (where transfer runs, transfer.py:104-105):
   * `batched=True` (default) feeds all d driving frames through ONE keypoint-detector call (D = d) and ONE generator
@@ -74,6 +75,26 @@ def transfer_one(generator, kp_detector, source_image, driving_video, transfer_p
     out['kp_driving'] = kp_driving
     out['kp_source'] = kp_source
     out['kp_norm'] = kp_driving_norm
+    return out
+
+
+def reconstruct(generator, kp_detector, video, batched=True):
+    """reconstruction.py:12-25,57-62: frame 0 of `video` (B,C,d,H,W) is the appearance, every frame is a driving
+    frame.  Returns the reference's dictionary: 'video_prediction' / 'video_deformed' (B,C,d,H,W), 'kp_driving',
+    'kp_source'.  `batched` as in transfer_one (eval mode: identical results, one KP pass + one generator pass)."""
+    d = video.shape[2]
+    source = video[:, :, :1]
+    kp_source = kp_detector(source)
+    if batched:
+        kp_video = kp_detector(video)
+        out = dict(generator(source, kp_driving=kp_video, kp_source=kp_source))
+    else:
+        kp_video = _cat_dict([kp_detector(video[:, :, i:(i + 1)]) for i in range(d)], dim=1)
+        parts = [generator(source, kp_driving={k: v[:, i:(i + 1)] for k, v in kp_video.items()}, kp_source=kp_source)
+                 for i in range(d)]
+        out = {k: torch.cat([p[k] for p in parts], dim=2) for k in ('video_prediction', 'video_deformed')}
+    out['kp_driving'] = kp_video
+    out['kp_source'] = kp_source
     return out
 
 

@@ -78,8 +78,55 @@ def run_reference(cfg, res, batch, store_weights):
     return out
 
 
+def read_strip_png(path, image_shape=(64, 64, 3)):
+    """frames_dataset.py:14-29 (read_video, .png branch) restated with PIL: a W*T x H strip -> (T, H, W, 3) float32."""
+    from PIL import Image
+    image = np.array(Image.open(path))
+    if image.ndim == 2:
+        image = np.stack([image] * 3, -1)
+    if image.shape[2] == 4:
+        image = image[..., :3]
+    video = np.moveaxis(image, 1, 0).reshape((-1,) + image_shape)
+    return np.moveaxis(video, 1, 2)  # uint8; img_as_float32 == / 255
+
+
+def run_reconstruction(cfg, png):
+    """BASELINE.json configs[0] (PR1): config/shapes.yaml as shipped, eval mode, seed-0 default-init weights (+ the
+    seeded flow-head perturbation so the warp is not the identity), reconstruction of one bundled data/shapes test
+    video (32 frames 64x64, B=1) by the reference's OWN `generate` (reconstruction.py:12-25, body extracted from the
+    unmodified file) around the reference's own modules, keypoints as in reconstruction.py:57-62."""
+    import ast
+    torch.manual_seed(0)
+    gen, disc, kp = ref_shim.build_from_config(cfg)
+    helpers.perturb_flow_head(gen)
+    src = open(os.path.join(ref_shim.REF_ROOT, 'reconstruction.py')).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'generate']
+    ns = {'torch': torch}
+    exec(compile(ast.Module(body=fn, type_ignores=[]), 'reference/reconstruction.py', 'exec'), ns)
+    frames = read_strip_png(png)
+    video = torch.from_numpy(frames.astype(np.float32) / 255.0).permute(3, 0, 1, 2)[None].contiguous()  # (1,3,T,H,W)
+    for m in (gen, kp):
+        m.eval()
+    cat_dict = lambda l, dim: {k: torch.cat([v[k] for v in l], dim=dim) for k in l[0]}
+    with torch.no_grad():
+        kp_appearance = kp(video[:, :, :1])
+        kp_video = cat_dict([kp(video[:, :, i:(i + 1)]) for i in range(video.shape[2])], dim=1)
+        out = ns['generate'](gen, appearance_image=video[:, :, :1], kp_appearance=kp_appearance, kp_video=kp_video)
+    keep = [0, 7, 16, 31]
+    return {'frames_u8': frames, 'checksum': np.array([checksum(gen.state_dict()), checksum(kp.state_dict())]),
+            'kp_mean': kp_video['mean'].numpy(), 'kp_var': kp_video['var'].numpy(), 'keep': np.array(keep),
+            'video_prediction': out['video_prediction'][:, :, keep].numpy(),
+            'video_deformed': out['video_deformed'][:, :, keep].numpy()}
+
+
 def main():
     os.makedirs(os.path.join(ROOT, 'tests', 'golden'), exist_ok=True)
+    recon = run_reconstruction(helpers.load_config('shapes'),
+                               os.path.join(ref_shim.REF_ROOT, 'data', 'shapes', 'test', '00000001.png'))
+    np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'golden_recon_shapes.npz'), **recon)
+    print('golden_recon_shapes.npz', os.path.getsize(os.path.join(ROOT, 'tests', 'golden', 'golden_recon_shapes.npz')) // 1024, 'KiB')
+    if '--recon-only' in sys.argv:
+        return
     tiny = run_reference(helpers.tiny_config(), 32, 2, True)
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'golden_tiny.npz'), **tiny)
     shapes = run_reference(helpers.load_config('shapes'), 64, 2, False)

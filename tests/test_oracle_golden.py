@@ -43,6 +43,42 @@ def test_oracle_matches_golden_shapes_and_init_parity():
     print(rep)
 
 
+def recon_inputs(gold):
+    """(1,3,T,H,W) float video of the bundled data/shapes test strip stored in the fixture as uint8 frames."""
+    return torch.from_numpy(gold['frames_u8'].astype('float32') / 255.0).permute(3, 0, 1, 2)[None].contiguous()
+
+
+def test_oracle_reconstruction_matches_reference_on_bundled_shapes_video():
+    """BASELINE.json configs[0]: shapes.yaml, eval, B=1, the 32-frame bundled test video, against the fixture made by
+    the reference's own `generate` (oracle/make_golden.py:run_reconstruction)."""
+    gold = helpers.load_golden('golden_recon_shapes')
+    cfg = helpers.load_config('shapes')
+    from modules.generator import MotionTransferGenerator
+    from modules.discriminator import Discriminator
+    from modules.keypoint_detector import KPDetector
+    mp = cfg['model_params']
+    torch.manual_seed(0)
+    pg = MotionTransferGenerator(**mp['generator_params'], **mp['common_params'])
+    Discriminator(**mp['discriminator_params'], **mp['common_params'])  # consumes the RNG exactly like run.py:50-63
+    pk = KPDetector(**mp['kp_detector_params'], **mp['common_params'])
+    helpers.perturb_flow_head(pg)
+    helpers.assert_checksums([helpers.state_checksum(pg.state_dict()), helpers.state_checksum(pk.state_dict())],
+                             gold['checksum'])
+    og, od, ok = mo.build_from_config(cfg)
+    og.load_state_dict(pg.state_dict()); ok.load_state_dict(pk.state_dict())
+    for m in (og, ok):
+        m.eval()
+    with torch.no_grad():
+        out = mo.reconstruct(og, ok, recon_inputs(gold))
+    keep = gold['keep'].tolist()
+    assert helpers.max_abs(out['kp_driving']['mean'], torch.from_numpy(gold['kp_mean'])) < 1e-6
+    assert helpers.max_abs(out['kp_driving']['var'], torch.from_numpy(gold['kp_var'])) < 1e-6
+    assert helpers.max_abs(out['video_prediction'][:, :, keep], torch.from_numpy(gold['video_prediction'])) < 1e-5
+    # the warped SOURCE frame has 0 -> 1 edges between neighbouring pixels: 1e-6-pixel coordinate differences of the
+    # resized grid (batched vs per-frame evaluation order) show up as 1e-5 intensity differences on edge pixels
+    assert helpers.max_abs(out['video_deformed'][:, :, keep], torch.from_numpy(gold['video_deformed'])) < 1e-4
+
+
 def test_synthetic_inputs_are_reproducible():
     gold = helpers.load_golden('golden_tiny')
     assert torch.equal(helpers.smooth_frames(2, 1, 32, 5), torch.from_numpy(gold['source']))
