@@ -90,6 +90,12 @@ int mk_conv2d(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int u
 int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups, const float* wpack_tc, int R,
                  int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act, float slope,
                  float* y, int Cout_p, int ldy, void* stream);
+/* Dry runs of the two tensor-core entry points' host-side planning (tiling, split-K / pixel splits, ring depths,
+ * shared-memory and TMEM budgets); they touch no device state and work without a GPU (148 SMs assumed).  out[16]:
+ * see csrc/conv_tc.cu / csrc/wgrad_tc.cu.  tests/test_tc_plans.py sweeps every layer of the shipped configs. */
+int mk_conv2d_tc_plan(int N, int Hin, int Win, int Cin_p, int ups, int R, int S, int pad, int act, int Cout_p, int ldy,
+                      int* out);
+int mk_conv2d_wgrad_tc_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int R, int S, int pad, int* out);
 /* EXPERIMENTAL, opt-in (MONKEY_B200_CONV_HALO=1), not yet validated on hardware: same contract as mk_conv2d_tc for
  * stride-1 3x3 / 4x4 convolutions without upsample on maps of at least 8 x (16-(S-1)) pixels, but the tile's halo is
  * staged ONCE per channel chunk and every tap reads it as a row-shifted window (csrc/conv_tc_halo.cu).  Returns -2

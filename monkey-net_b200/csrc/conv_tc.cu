@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
 
 }  // namespace
 
+static thread_local int* t_plan_out = nullptr;  // set by mk_conv2d_tc_plan for a dry run
+
 // Returns 0 on success, -2 if the shape is outside this kernel's envelope (caller uses mk_conv2d instead).
 MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
                            const float* wpack_tc, int R, int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
@@ -195,8 +197,6 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
         mk_set_error("mk_conv2d_tc: unsupported channel configuration");
         return -2;
     }
-    EncodeTiledFn encode = get_encode();
-    MK_REQUIRE(encode != nullptr, "mk_conv2d_tc: cuTensorMapEncodeTiled unavailable");
     TcP p;
     p.ups = ups ? 1 : 0;
     if (p.ups) {
@@ -243,6 +243,16 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     if (nst < 2) nst = 2;
     p.nstages = nst;
     const int smem_bytes = p.nstages * p.stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    MK_REQUIRE(smem_bytes <= SMEM_MAX, "mk_conv2d_tc: shared memory plan exceeds 227 KB (%d)", smem_bytes);
+    if (t_plan_out) {  // dry run (mk_conv2d_tc_plan): report the launch plan, touch no device state
+        int* o = t_plan_out;
+        o[0] = p.tilesW * p.tilesH * tilesN; o[1] = grid_y; o[2] = (p.ups ? 4 : 1) * p.ksplit; o[3] = smem_bytes;
+        o[4] = p.nstages; o[5] = p.ksplit; o[6] = p.iters_per_split; o[7] = niter_total; o[8] = p.tmem_cols;
+        o[9] = p.TW; o[10] = p.TH; o[11] = p.TN; o[12] = b_rows; o[13] = p.stage_bytes; o[14] = p.Ho; o[15] = p.Wo;
+        return 0;
+    }
+    EncodeTiledFn encode = get_encode();
+    MK_REQUIRE(encode != nullptr, "mk_conv2d_tc: cuTensorMapEncodeTiled unavailable");
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin_p, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
@@ -278,4 +288,18 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     dim3 grid((unsigned)(p.tilesW * p.tilesH * tilesN), (unsigned)grid_y, (unsigned)((p.ups ? 4 : 1) * p.ksplit));
     k_conv_tc<<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
     return mk_check_launch("mk_conv2d_tc");
+}
+
+// Dry run of mk_conv2d_tc's host-side planning (no device state touched, works without a GPU: 148 SMs assumed):
+// out[16] = grid.x, grid.y, grid.z, dynamic smem bytes, ring stages, ksplit, K iterations per split, K iterations,
+// TMEM columns, TMA box TW, TH, TN, weight rows per stage, stage bytes, Ho, Wo.  tests/test_tc_plans.py sweeps every
+// layer shape of the shipped configurations through it.
+MK_EXPORT int mk_conv2d_tc_plan(int N, int Hin, int Win, int Cin_p, int ups, int R, int S, int pad, int act, int Cout_p,
+                                int ldy, int* out) {
+    MK_REQUIRE(out != nullptr, "mk_conv2d_tc_plan: out is NULL");
+    t_plan_out = out;
+    const int rc = mk_conv2d_tc(nullptr, N, Hin, Win, Cin_p, Cin_p, ups, nullptr, R, S, pad, nullptr, nullptr, nullptr, 0,
+                                act, 0.f, nullptr, Cout_p, ldy, nullptr);
+    t_plan_out = nullptr;
+    return rc;
 }

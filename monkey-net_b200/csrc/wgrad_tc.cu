@@ -180,14 +180,14 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
 
 }  // namespace
 
+static thread_local int* t_wplan_out = nullptr;  // set by mk_conv2d_wgrad_tc_plan for a dry run
+
 MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,
                                  int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream) {
     if (Cin_p % 4 || Cout_p % 4 || ldx % 4 || ldy % 4) {
         mk_set_error("mk_conv2d_wgrad_tc: unsupported channel configuration");
         return -2;
     }
-    EncodeTiledFn encode = get_encode();
-    MK_REQUIRE(encode != nullptr, "mk_conv2d_wgrad_tc: cuTensorMapEncodeTiled unavailable");
     WgTcP p;
     p.N = N; p.Ho = Hin + 2 * pad - R + 1; p.Wo = Win + 2 * pad - S + 1;
     MK_REQUIRE(p.Ho > 0 && p.Wo > 0, "mk_conv2d_wgrad_tc: empty output");
@@ -236,6 +236,16 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
     if (ring_bytes < a_reach) ring_bytes = a_reach;
     const int smem_bytes = ring_bytes + 1024 /*align*/;
     MK_REQUIRE(smem_bytes <= WSMEM_MAX, "mk_conv2d_wgrad_tc: shared memory plan exceeds 227 KB (%d)", smem_bytes);
+    if (t_wplan_out) {  // dry run (mk_conv2d_wgrad_tc_plan)
+        int* o = t_wplan_out;
+        o[0] = co_tiles; o[1] = p.n_tap_groups * p.n_ci_tiles; o[2] = (int)splits; o[3] = smem_bytes;
+        o[4] = p.a_slots; o[5] = p.b_slots; o[6] = p.taps_per_cta; o[7] = p.npad; o[8] = p.tmem_cols;
+        o[9] = p.TW; o[10] = p.TH; o[11] = p.TN; o[12] = p.nchunks; o[13] = p.chunks_per_split; o[14] = p.na_max;
+        o[15] = p.nb_max;
+        return 0;
+    }
+    EncodeTiledFn encode = get_encode();
+    MK_REQUIRE(encode != nullptr, "mk_conv2d_wgrad_tc: cuTensorMapEncodeTiled unavailable");
 
     CUtensorMap tmDy, tmX;
     cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TN};
@@ -270,4 +280,16 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
     dim3 grid((unsigned)co_tiles, (unsigned)(p.n_tap_groups * p.n_ci_tiles), (unsigned)splits);
     k_wgrad_tc<<<grid, 256, smem_bytes, st>>>(tmDy, tmX, p);
     return mk_check_launch("mk_conv2d_wgrad_tc");
+}
+
+// Dry run of mk_conv2d_wgrad_tc's host-side planning (see mk_conv2d_tc_plan): out[16] = grid.x (co tiles), grid.y
+// (tap groups x ci tiles), grid.z (pixel splits), dynamic smem bytes, A ring slots, B ring slots, taps per CTA,
+// accumulator columns per tap, TMEM columns, TMA box TW, TH, TN, pixel chunks, chunks per split, A boxes, B boxes.
+MK_EXPORT int mk_conv2d_wgrad_tc_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int R, int S, int pad, int* out) {
+    MK_REQUIRE(out != nullptr, "mk_conv2d_wgrad_tc_plan: out is NULL");
+    t_wplan_out = out;
+    const int rc = mk_conv2d_wgrad_tc(nullptr, N, Hin, Win, Cin_p, Cin_p, nullptr, Cout_p, Cout_p, R, S, pad, nullptr,
+                                      nullptr);
+    t_wplan_out = nullptr;
+    return rc;
 }

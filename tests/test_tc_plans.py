@@ -1,0 +1,91 @@
+"""Host-side launch planning of the tensor-core kernels (mk_conv2d_tc_plan / mk_conv2d_wgrad_tc_plan: the same code the
+real entry points run, as a dry run that needs no GPU) swept over EVERY convolution of the eight shipped configurations
+at the resolutions / batch sizes of BASELINE.json - forward, input-gradient and weight-gradient shapes, with the padded
+channel counts the NHWC layout produces.  Checks the invariants the kernels rely on: shared memory within 227 KB, ring
+depths, TMEM columns, TMA box limits, split coverage without empty CTAs."""
+import ctypes
+
+import pytest
+import torch
+
+import helpers
+from oracle import monkey_oracle as mo
+
+CASES = [('shapes', 64, 32), ('taichi', 64, 32), ('taichi', 256, 8), ('moving-gif', 256, 16), ('vox-full', 256, 16),
+         ('vox', 256, 4), ('nemo', 64, 32), ('bair', 64, 32), ('actions', 64, 32)]
+
+
+def pad4(c):
+    return (c + 3) & ~3
+
+
+def conv_shapes(name, res):
+    """(cin, cout, k, pad, H, W, frames_per_sample, upsampled) of every conv of KP detector (D=2), generator and
+    discriminator, from forward hooks on the oracle."""
+    cfg = helpers.load_config(name)
+    og, od, ok = mo.build_from_config(cfg)
+    for m in (og, od, ok):
+        for p in m.parameters():
+            torch.nn.init.normal_(p, std=0.01)
+        m.eval()
+    shapes = []
+
+    def hook(m, inp, out):
+        x = inp[0]
+        co, cig, _, kh, kw = m.weight.shape
+        groups = x.shape[1] // cig
+        shapes.append((x.shape[1], co, kh, (kh - 1) // 2 if out.shape[-1] == x.shape[-1] else 0, x.shape[-2],
+                       x.shape[-1], x.shape[0] * x.shape[2], groups))
+    hs = [m.register_forward_hook(hook) for mod in (og, od, ok) for m in mod.modules() if isinstance(m, mo._Conv)]
+    x = torch.rand(1, 3, 1, res, res)
+    with torch.no_grad():
+        kpj = ok(torch.cat([x, x], 2))
+        kd, ks = {k: v[:, 1:] for k, v in kpj.items()}, {k: v[:, :1] for k, v in kpj.items()}
+        g = og(x, kd, ks)
+        od(g['video_prediction'], kd, ks)
+    for h in hs:
+        h.remove()
+    return shapes
+
+
+def plan(lib, fn, *args):
+    out = (ctypes.c_int * 16)()
+    rc = getattr(lib, fn)(*args, out)
+    return rc, list(out)
+
+
+@pytest.mark.parametrize('name,res,batch', CASES)
+def test_every_layer_has_a_valid_tensor_core_plan(name, res, batch):
+    from monkey_net_b200 import lib as mklib
+    lib = mklib.load()
+    n_layers = 0
+    for cin, cout, k, pad, H, W, frames, groups in conv_shapes(name, res):
+        N = frames * batch
+        for cin_p in {pad4(cin), pad4(cin) + 4}:          # dense and concat-with-holes layouts
+            cop = pad4(cout)
+            ho, wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+            # forward (act 0 and a fused activation), input gradient (full correlation), weight gradient
+            jobs = [('fwd', (N, H, W, cin_p, 0, k, k, pad, 0, cop, cop)), ('fwd_act', (N, H, W, cin_p, 0, k, k, pad, 1, cop, cop)),
+                    ('dgrad', (N, ho, wo, cop, 0, k, k, k - 1 - pad, 0, cin_p, cin_p))]
+            if k == 3 and groups == 1 and H % 2 == 0 and W % 2 == 0:
+                # the same conv as the sub-pixel form of UpBlock3D (nearest x2 folded in): low-resolution input
+                jobs.append(('ups', (N, H // 2, W // 2, cin_p, 1, 3, 3, 1, 0, cop, cop)))
+            for tag, a in jobs:
+                rc, o = plan(lib, 'mk_conv2d_tc_plan', *a)
+                assert rc == 0, (name, tag, a, lib.mk_last_error())
+                gx, gy, gz, smem, nst, ksplit, ips, niter, tmem, tw, th, tn, b_rows, stage, oh, ow = o
+                assert smem <= 227 * 1024 and 2 <= nst <= 8 and nst * stage + 1280 == smem
+                assert tmem in (32, 64, 128) and b_rows <= tmem and tw * th * tn == 128 and max(tw, th, tn) <= 256
+                assert ksplit >= 1 and ips * ksplit >= niter and ips * (ksplit - 1) < niter      # no empty split
+                assert gx < 2 ** 31 and gy <= 65535 and gz <= 65535
+                if tag == 'fwd_act':
+                    assert ksplit == 1                                                            # linear epilogue only
+            rc, o = plan(lib, 'mk_conv2d_wgrad_tc_plan', N, H, W, cin_p, cop, k, k, pad)
+            assert rc == 0, (name, 'wgrad', lib.mk_last_error())
+            gx, gy, gz, smem, a_slots, b_slots, taps, npad, tmem, tw, th, tn, nchunks, cps, na, nb = o
+            assert smem <= 227 * 1024 and 1 <= a_slots <= 4 and 2 <= b_slots <= 12
+            assert taps * npad <= 512 and tmem in (32, 64, 128, 256, 512) and taps * npad <= tmem
+            assert tw * th * tn == 64 and cps * gz >= nchunks and cps * (gz - 1) < nchunks
+            assert gy * taps >= k * k and gz <= 65535
+            n_layers += 1
+    assert n_layers > 40
