@@ -30,6 +30,16 @@ static inline int mk_num_sms() {
 
 static inline long long mk_cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per function AND per device: remember, per kernel, on which devices it has been applied
+// (`done` is that kernel's static mask).  One process drives one GPU in this design, but a process that touches a
+// second device must not launch with the first device's attribute state.
+static inline unsigned long long mk_attr_needed(unsigned long long done) {  // 0 = already applied on this device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (done & bit) ? 0ull : bit;
+}
+
 // ---------------------------------------------------------------------------------------------- device helpers
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

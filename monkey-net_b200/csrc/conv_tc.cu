@@ -274,11 +274,11 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc: weight tensor map rejected (%d)", (int)r);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_done = 0;
+    if (const unsigned long long attr_bit = mk_attr_needed(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
         if (e != cudaSuccess) { mk_set_error("mk_conv2d_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
+        attr_done |= attr_bit;
     }
     if (p.ksplit > 1) {
         const size_t out_pix = (size_t)N * p.Ho * p.Wo * (p.ups ? 4 : 1);

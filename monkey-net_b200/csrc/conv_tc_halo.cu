@@ -247,11 +247,11 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: weight tensor map rejected (%d)", (int)r);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_done = 0;
+    if (const unsigned long long attr_bit = mk_attr_needed(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(k_conv_tc_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_MAX);
         if (e != cudaSuccess) { mk_set_error("mk_conv2d_tc_halo: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
+        attr_done |= attr_bit;
     }
     dim3 grid((unsigned)(p.tilesW * p.tilesH * N), (unsigned)((Cout_p + 127) / 128), 1);
     k_conv_tc_halo<<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);

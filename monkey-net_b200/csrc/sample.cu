@@ -306,11 +306,11 @@ template <int V, int GS_STAGES>
 static int launch_gs_async(const float* inp, int B, int h, int w, int Cp, int ld, const float* deform, int d, int h0,
                            int w0, int mode, float* out, int ldo, cudaStream_t st) {
     const int smem = 8 * GS_STAGES * 4 * V * 32 * (int)sizeof(float4);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_done = 0;
+    if (const unsigned long long attr_bit = mk_attr_needed(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(k_grid_sample_fwd_async<V, GS_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { mk_set_error("mk_grid_sample_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
+        attr_done |= attr_bit;
     }
     int resident = (227 * 1024 / (smem + 1024)) * 8;  // warps per SM by shared memory
     if (resident > 40) resident = 40;                 // ... and by registers

@@ -267,11 +267,11 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
         MK_REQUIRE(rc == CUDA_SUCCESS, "mk_conv2d_wgrad_tc: x tensor map rejected (%d)", (int)rc);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_done = 0;
+    if (const unsigned long long attr_bit = mk_attr_needed(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, WSMEM_MAX);
         if (e != cudaSuccess) { mk_set_error("mk_conv2d_wgrad_tc: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_set = true;
+        attr_done |= attr_bit;
     }
     if (splits > 1) {
         cudaError_t e = cudaMemsetAsync(dwpack, 0, sizeof(float) * (size_t)R * S * Cin_p * Cout_p, st);
