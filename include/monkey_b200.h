@@ -218,9 +218,11 @@ int mk_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
 /* Adam over ONE flat parameter group, CUDA-graph capturable (train.py:81-83: betas (0.5, 0.999), eps 1e-8, no weight
  * decay; update identical to torch.optim.Adam).  p, g, m, v: flat fp32 buffers of n elements (16-byte aligned);
  * *step (device int64) is the number of updates done so far and is advanced by the kernel; *ticket (device uint32,
- * zero-initialised) is scratch.  zero_grad != 0 clears g in the same pass (optimizer.zero_grad() of train.py:118). */
+ * zero-initialised) is scratch.  zero_grad != 0 clears g in the same pass (optimizer.zero_grad() of train.py:118).
+ * lr_dev (device float, may be NULL): when given it overrides `lr`, so a captured CUDA graph follows the
+ * MultiStepLR schedule of train.py:92-97,146-148 without re-capture. */
 int mk_adam_flat(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                 long long* step, unsigned* ticket, int zero_grad, void* stream);
+                 long long* step, unsigned* ticket, int zero_grad, const float* lr_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -188,7 +188,11 @@ MK_EXPORT int mk_adam_step(float* p, const float* g, float* m, float* v, long lo
 // read it by then.  torch.optim.Adam(capturable=True) spends ~450 launches per training iteration on the same work.
 __global__ void __launch_bounds__(256) k_adam_flat(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, float lr, float b1, float b2,
-                                                   float eps, long long* step, unsigned* ticket, int zero_grad) {
+                                                   float eps, long long* step, unsigned* ticket, int zero_grad,
+                                                   const float* __restrict__ lr_dev) {
+    // the learning rate of a CAPTURED step must be a device scalar too: MultiStepLR (train.py:92-97,146-148) changes it
+    // between epochs and a graph replays the kernel arguments it was captured with
+    if (lr_dev) lr = *lr_dev;
     const long long t = *reinterpret_cast<volatile long long*>(step) + 1;
     const float bc1 = (float)(1.0 - pow((double)b1, (double)t));
     const float bc2 = (float)(1.0 - pow((double)b2, (double)t));
@@ -227,7 +231,8 @@ __global__ void __launch_bounds__(256) k_adam_flat(float* __restrict__ p, float*
 }
 
 MK_EXPORT int mk_adam_flat(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                           float eps, long long* step, unsigned* ticket, int zero_grad, void* stream) {
+                           float eps, long long* step, unsigned* ticket, int zero_grad, const float* lr_dev,
+                           void* stream) {
     if (n <= 0) return 0;
     MK_REQUIRE(step != nullptr && ticket != nullptr, "mk_adam_flat: step / ticket must be device pointers");
     long long blocks = mk_cdiv(mk_cdiv(n, 4), 256);
@@ -235,7 +240,7 @@ MK_EXPORT int mk_adam_flat(float* p, float* g, float* m, float* v, long long n, 
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     k_adam_flat<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, ticket,
-                                                                   zero_grad);
+                                                                   zero_grad, lr_dev);
     return mk_check_launch("mk_adam_flat");
 }
 

@@ -516,6 +516,14 @@ class _NormAct(torch.autograd.Function):
                 else:
                     local = sums
                 dbeta, dgamma = local[:C], local[Cp:Cp + C]
+        elif mode == 'bn' and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+            # eval-mode BN with trainable affine parameters (fine-tuning with frozen statistics): F.batch_norm(
+            # training=False) still yields dgamma = sum dz*xhat, dbeta = sum dz with xhat from the RUNNING statistics -
+            # exactly what the reduce kernel computes from the eval parameter block.  dx needs no sums in this mode.
+            esums = _empty(2 * Cp, like=x)
+            lib.call('mk_norm_bwd_reduce', x.data_ptr(), Cp, dout.data_ptr(), ctot, N, H, W, Cp, params.data_ptr(),
+                     0, slope, pool, esums.data_ptr(), st)
+            dbeta, dgamma = esums[:C], esums[Cp:Cp + C]
         dx = None
         if ctx.needs_input_grad[0]:
             dx = _empty(N, H, W, Cp, like=x)
@@ -771,6 +779,15 @@ class _Embed(torch.autograd.Function):
         return None, d_kd_mean, d_kd_var, d_ks_mean, d_ks_var, None
 
 
+def _require_single_source_frame(ks_mean):
+    """The kernels index kp_source as (B,1,K,..) - every caller of the reference passes the d=1 source keypoints
+    (train.py:14-21 `v[:, :1]`, transfer.py:67, reconstruction.py:16).  The reference would broadcast a d>1 source
+    against the driving frames; that never-used case is rejected instead of silently reading the wrong keypoints."""
+    if ks_mean.dim() != 4 or ks_mean.shape[1] != 1:
+        raise NotImplementedError('monkey-net_b200: kp_source must hold exactly one frame (B,1,K,2), got %s'
+                                  % (tuple(ks_mean.shape),))
+
+
 def movement_embed(src, kp_driving, kp_source, h, w, num_channels, kp_variance, use_heatmap, use_difference,
                    use_deformed, add_bg, heatmap_type, norm_const):
     """movement_embedding.py:42-92 -> Act [B*d,h,w,pad4(slots*F)], channels slot-major / feature-minor."""
@@ -784,6 +801,7 @@ def movement_embed(src, kp_driving, kp_source, h, w, num_channels, kp_variance, 
         var_mode, const_var = 2, float(kp_variance)
     nc = 0.0 if norm_const == 'sum' else float(norm_const)
     kd_mean, ks_mean = _kp_c(kp_driving['mean']), _kp_c(kp_source['mean'])
+    _require_single_source_frame(ks_mean)
     kd_var = _kp_c(kp_driving['var']) if var_mode != 2 and use_heatmap else None
     ks_var = _kp_c(kp_source['var']) if var_mode != 2 and use_heatmap else None
     cfg = (flags, var_mode, const_var, nc, num_channels, h, w)
@@ -823,8 +841,9 @@ class _FlowHead(torch.autograd.Function):
 
 def flow_head(a, kp_driving, kp_source, use_mask, use_correction):
     """dense_motion_module.py:52-76 -> deformation [B*d,h,w,2] (the zero z column is added at the API edge)."""
-    return _FlowHead.apply(a.t, _kp_c(kp_driving['mean']), _kp_c(kp_source['mean']), int(bool(use_mask)),
-                           int(bool(use_correction)))
+    ks_mean = _kp_c(kp_source['mean'])
+    _require_single_source_frame(ks_mean)
+    return _FlowHead.apply(a.t, _kp_c(kp_driving['mean']), ks_mean, int(bool(use_mask)), int(bool(use_correction)))
 
 
 # ====================================================================================================== losses

@@ -24,7 +24,12 @@ class FlatAdam:
         dev = self.params[0].device
         if dev.type != 'cuda':
             raise RuntimeError('monkey-net_b200: FlatAdam needs CUDA parameters - the B200 path has no CPU fallback')
-        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
+        # the learning rate lives in DEVICE memory: a captured graph replays fixed kernel arguments, so a host float
+        # would freeze MultiStepLR (train.py:92-97,146-148) at its capture-time value
+        self._lr = float(lr)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self.param_groups = [{'lr': float(lr), 'initial_lr': float(lr), 'betas': self.betas, 'eps': self.eps}]
         # every parameter starts on a 16-byte boundary so the kernel's float4 path never straddles two tensors' tails
         offs, total = [], 0
         for p in self.params:
@@ -46,6 +51,17 @@ class FlatAdam:
                 p.grad = self.flat_g[off:off + n].view(p.shape)
 
     # ------------------------------------------------------------------ torch.optim-like surface
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        """host-side schedule update: one tiny H2D fill outside the graph, the captured step reads the new value"""
+        self._lr = float(value)
+        self.param_groups[0]['lr'] = self._lr
+        self.lr_dev.fill_(self._lr)
+
     def intact(self):
         lo, hi = self.flat_g.data_ptr(), self.flat_g.data_ptr() + 4 * self.n
         plo, phi = self.flat_p.data_ptr(), self.flat_p.data_ptr() + 4 * self.n
@@ -62,7 +78,7 @@ class FlatAdam:
         lib.call('mk_adam_flat', self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
                  self.exp_avg_sq.data_ptr(), self.n, self.lr, self.betas[0], self.betas[1], self.eps,
                  self.step_count.data_ptr(), self._ticket.data_ptr(), 1 if zero_grad else 0,
-                 torch.cuda.current_stream().cuda_stream)
+                 self.lr_dev.data_ptr(), torch.cuda.current_stream().cuda_stream)
         from . import ops
         ops.note_parameters_changed()  # in-place update through raw pointers: invalidate cached inference packs
 
@@ -77,4 +93,26 @@ class FlatAdam:
 
     def load_state_dict(self, sd):
         self.exp_avg.copy_(sd['exp_avg']); self.exp_avg_sq.copy_(sd['exp_avg_sq']); self.step_count.copy_(sd['step'])
-        self.lr, self.betas, self.eps = float(sd['lr']), tuple(sd['betas']), float(sd['eps'])
+        self.betas, self.eps = tuple(sd['betas']), float(sd['eps'])
+        self.lr = float(sd['lr'])
+
+
+class MultiStepLR:
+    """torch.optim.lr_scheduler.MultiStepLR for FlatAdam (torch's class insists on a torch Optimizer): same schedule
+    as train.py:92-97 - lr = initial_lr * gamma ** (number of milestones <= epoch), `step()` once per epoch
+    (train.py:146-148).  The new rate is written into the optimiser's device scalar, so a captured training graph
+    picks it up on its next replay."""
+
+    def __init__(self, optimizer, milestones, gamma=0.1, last_epoch=-1):
+        self.optimizer, self.milestones, self.gamma = optimizer, sorted(int(m) for m in milestones), float(gamma)
+        self.base_lr = optimizer.param_groups[0]['initial_lr']
+        self.last_epoch = last_epoch
+        self.step()
+
+    def get_last_lr(self):
+        return [self.optimizer.lr]
+
+    def step(self):
+        self.last_epoch += 1
+        k = sum(1 for m in self.milestones if m <= self.last_epoch)
+        self.optimizer.lr = self.base_lr * self.gamma ** k

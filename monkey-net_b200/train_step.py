@@ -150,6 +150,15 @@ class GraphedTrainer:
                 self.grad_sync = (mkdist.FlatGradSync(generator.parameters()),
                                   mkdist.FlatGradSync(discriminator.parameters()),
                                   mkdist.FlatGradSync(kp_detector.parameters()))
+        # MultiStepLR of train.py:92-97 (one scheduler per optimiser, stepped once per epoch, train.py:146-148)
+        self.schedulers = None
+        ms = train_params.get('epoch_milestones') if hasattr(train_params, 'get') else None
+        if ms is not None:
+            if self.fused_adam:
+                from .optim import MultiStepLR
+            else:
+                from torch.optim.lr_scheduler import MultiStepLR
+            self.schedulers = [MultiStepLR(o, ms, gamma=0.1) for o in self.optimizers]
         self.use_graph, self.warmup = bool(use_graph), warmup
         self.graph = None
         self.static_in = self.static_out = None
@@ -202,6 +211,17 @@ class GraphedTrainer:
             self.static_out = self._iteration(self.static_in)
         self.kernels_per_step = lib.launches() - n0  # C-ABI kernel launches recorded into the graph
         self.graph = graph
+
+    def epoch_end(self):
+        """scheduler_*.step() of train.py:146-148.  With FlatAdam the rate is a device scalar, so the captured graph
+        follows the schedule; torch.optim.Adam(capturable=True) keeps lr as a tensor only if it was created as one -
+        that path re-captures."""
+        if self.schedulers is None:
+            return
+        for s in self.schedulers:
+            s.step()
+        if not self.fused_adam and self.graph is not None:
+            self.graph = None  # host-float lr baked into the captured foreach kernels: capture again
 
     def step(self, x):
         """x = {'source': (B,3,1,H,W), 'video': (B,3,1,H,W)} on this device or in (pinned) host memory.  Returns the

@@ -138,10 +138,27 @@ class GraphedTransfer:
             self.static_out = self._call(*self.static_in)
         self.kernels_per_call = lib.launches() - n0
         self.graph = graph
+        # The captured kernels read the CACHED weight packs / folded eval-BN vectors (ops._INFER_CACHE), not the live
+        # parameters: keep those tensors alive for the life of the graph (a later eager call may replace the cache
+        # entries, and a freed pack would be recycled by the allocator under the graph's feet) and remember the
+        # parameter state they were built from.
+        from . import ops
+        self._pinned = list(ops._INFER_CACHE.values())
+        self._state = self._param_state()
+
+    def _param_state(self):
+        from . import ops
+        vers = 0
+        for m in (self.generator, self.kp_detector):
+            for t in list(m.parameters()) + list(m.buffers()):
+                vers += t._version
+        return (ops._PARAM_EPOCH[0], vers)
 
     def run(self, source, driving):
         if not self.use_graph:
             return self._call(source.to(self.device, non_blocking=True), driving.to(self.device, non_blocking=True))
+        if self.graph is not None and self._param_state() != self._state:
+            self.graph = None  # load_state_dict / a training step / an optimiser update since capture: stale packs
         if self.graph is None:
             self._capture(source, driving)
         self.static_in[0].copy_(source, non_blocking=True)

@@ -15,6 +15,7 @@ from torch import nn
 import torch.distributed as dist
 
 _hooked = set()
+_synced = set()
 HOOKS_ENABLED = True   # monkey_net_b200.train_step.GraphedTrainer switches to one flat all-reduce per optimiser step
 
 
@@ -36,6 +37,23 @@ def _avg_hook(p):
     p.grad.div_(w)
 
 
+def broadcast_module_state(module, src=0):
+    """rank `src`'s parameters and buffers -> every rank, in place (each tensor once per process)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            if id(t) in _synced:
+                continue
+            _synced.add(id(t))
+            if t.dtype == torch.int64 and t.dim() == 0:   # num_batches_tracked: nccl/gloo want >= 1-D
+                buf = t.detach().reshape(1).clone()
+                dist.broadcast(buf, src=src)
+                t.copy_(buf[0])
+            else:
+                dist.broadcast(t.data, src=src)
+
+
 class DataParallelWithCallback(nn.Module):
     def __init__(self, module, device_ids=None, output_device=None, dim=0):
         super(DataParallelWithCallback, self).__init__()
@@ -46,6 +64,10 @@ class DataParallelWithCallback(nn.Module):
         self.device_ids = list(device_ids) if device_ids is not None else None
         self.dim = dim
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # The reference's DataParallel re-broadcasts the weights of device 0 to every replica on every forward
+            # (replicate.py:64-67) and neither run.py nor train.py seeds, so replicas may start from different random
+            # initialisations: rank 0's parameters and buffers become everybody's once, as DDP does at construction.
+            broadcast_module_state(module)
             for p in module.parameters():
                 if p.requires_grad and id(p) not in _hooked:
                     _hooked.add(id(p))

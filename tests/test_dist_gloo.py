@@ -156,6 +156,30 @@ def test_flat_gradsync_is_one_allreduce_over_views():
             assert torch.allclose(g, p.grad, atol=1e-6)
 
 
+def _facade_initial_state(rank, world):
+    from sync_batchnorm import DataParallelWithCallback
+    torch.manual_seed(100 + rank)                      # run.py / train.py do not seed: every rank draws its own init
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.BatchNorm1d(4))
+    with torch.no_grad():
+        net[1].running_mean.normal_()
+        net[1].num_batches_tracked.fill_(7 + rank)
+    DataParallelWithCallback(net)
+    return [t.detach().clone() for t in list(net.parameters()) + list(net.buffers())]
+
+
+def test_facade_broadcasts_rank0_parameters_and_buffers():
+    """replicas must start from rank 0's weights (DataParallel re-broadcasts them every forward in the
+    reference, sync_batchnorm/replicate.py:64-67); without it averaged gradients are applied to diverging replicas."""
+    a, b = _spawn(_facade_initial_state)
+    torch.manual_seed(100)
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.BatchNorm1d(4))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    for x, p in zip(a, ref.parameters()):
+        assert torch.equal(x, p.detach())
+    assert int(a[-1]) == int(b[-1]) == 7
+
+
 def test_facade_rejects_single_process_multi_device():
     from sync_batchnorm import DataParallelWithCallback
     with pytest.raises(RuntimeError, match='one-process-per-GPU'):

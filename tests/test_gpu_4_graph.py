@@ -110,3 +110,43 @@ def test_graphed_trainer_flat_adam_matches_torch_adam_first_step():
         diff = (p1.detach() - p2.detach()).abs()
         tot += diff.numel(); flips += int((diff > 0.5 * tp['lr']).sum())
     assert flips / tot < 1e-3, (flips, tot)
+
+
+def test_multistep_lr_reaches_the_captured_graph():
+    """MultiStepLR (train.py:92-97,146-148) under GraphedTrainer: the learning rate is a device scalar of FlatAdam, so
+    a decay between epochs changes the update of the ALREADY CAPTURED step (a host float would be frozen in the graph).
+    Adam's first updates have magnitude ~lr per entry, which makes the rate directly observable."""
+    from monkey_net_b200 import train_step
+    cfg = helpers.tiny_config()
+    tp = dict(cfg['train_params'])
+    tp['epoch_milestones'] = [1]
+    gen, disc, kp = _nets(cfg)
+    tr = train_step.GraphedTrainer(kp, gen, disc, tp, use_graph=True)
+    x = {'source': helpers.smooth_frames(4, 1, 32, 10).cuda(), 'video': helpers.smooth_frames(4, 1, 32, 20).cuda()}
+    w = gen.refinement_module[-1].weight
+    tr.step(x)                       # capture + first replay, epoch 0: lr
+    graph = tr.graph
+    w0 = w.detach().clone()
+    tr.step(x)
+    d_full = float((w.detach() - w0).abs().mean())
+    tr.epoch_end()                   # epoch 1 is a milestone: lr * 0.1
+    assert abs(tr.optimizers[0].lr - tp['lr'] * 0.1) < 1e-12
+    w1 = w.detach().clone()
+    tr.step(x)
+    d_decayed = float((w.detach() - w1).abs().mean())
+    assert tr.graph is graph, 'the schedule must not force a re-capture'
+    assert 0.03 < d_decayed / d_full < 0.3, (d_full, d_decayed)
+
+
+def test_flat_multistep_lr_matches_torch_schedule():
+    from monkey_net_b200.optim import FlatAdam, MultiStepLR
+    p = [torch.nn.Parameter(torch.randn(8, device='cuda'))]
+    q = [torch.nn.Parameter(torch.randn(8))]
+    a = FlatAdam(p, lr=2e-4, betas=(0.5, 0.999))
+    b = torch.optim.Adam(q, lr=2e-4, betas=(0.5, 0.999))
+    sa = MultiStepLR(a, [2, 5], gamma=0.1)
+    sb = torch.optim.lr_scheduler.MultiStepLR(b, [2, 5], gamma=0.1)
+    for _ in range(7):
+        assert abs(a.lr - b.param_groups[0]['lr']) < 1e-15
+        assert abs(float(a.lr_dev) - a.lr) < 1e-10
+        b.step(); sa.step(); sb.step()
