@@ -314,7 +314,7 @@ def run_ours(args):
                                  'note': 'MONKEY_B200_CONV=fp32: every convolution on the exact FFMA kernels'}
             del t2, g2, d2, k2
         finally:
-            mkops.set_conv_mode('tf32')
+            mkops.set_conv_mode(conv_mode)
     if world == 1 and not args.no_transfer:
         del trainer, gen, disc, kp
         torch.cuda.empty_cache()

@@ -58,6 +58,8 @@ int mk_add_channels(const float* src, int lds, float* dst, int ldd, long long np
  *   mode 1 (dgrad):    Kin = output channels, Kout = input channels,  tap flipped (R-1-r, S-1-s).
  *   mode 4:            sub-pixel forward pack for the upsampled 3x3 conv, [4 parities][4 taps][Kout_p][Kin_p], TF32.
  *   modes 2 / 3:       modes 0 / 1 in the tensor-core layout [R*S][Kout_p][Kin_p], rounded to TF32 (mk_conv2d_tc).
+ *   mode | 8 (with 2, 3, 4): 3xTF32 pack - wpack holds 2x the floats, the TF32 remainders lo = rna(w - hi) in the
+ *                      same layout behind the hi half (mk_conv2d_tc_x3).
  * `cin_map[Cin_p]` maps each PHYSICAL input channel to its logical index or -1 (padding / concat holes);
  * physical output channel j is logical j for j < Co, padding otherwise.  Grouped convs are packed block-diagonal. */
 int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int groups, const int* cin_map, int Cin_p,
@@ -90,9 +92,17 @@ int mk_conv2d(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int u
 int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups, const float* wpack_tc, int R,
                  int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act, float slope,
                  float* y, int Cout_p, int ldy, void* stream);
+/* 3xTF32 ("reference precision") variant of mk_conv2d_tc: every fp32 operand is split hi + lo (hi = rna_tf32(v),
+ * lo = rna_tf32(v - hi)) and A_lo*B_hi + A_hi*B_lo + A_hi*B_hi accumulate in the same TMEM tile - fp32-accurate
+ * products (2^-22 relative) at a third of the TF32 issue rate.  wpack_tc = mk_pack_weight mode (2|3|4) | 8: the lo
+ * half follows the hi half (2x the floats); the activation tile is split in shared memory by idle warps. */
+int mk_conv2d_tc_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups, const float* wpack_tc, int R,
+                    int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
+                    float slope, float* y, int Cout_p, int ldy, void* stream);
 /* Dry runs of the two tensor-core entry points' host-side planning (tiling, split-K / pixel splits, ring depths,
  * shared-memory and TMEM budgets); they touch no device state and work without a GPU (148 SMs assumed).  out[16]:
- * see csrc/conv_tc.cu / csrc/wgrad_tc.cu.  tests/test_tc_plans.py sweeps every layer of the shipped configs. */
+ * see csrc/conv_tc.cu / csrc/wgrad_tc.cu.  tests/test_tc_plans.py sweeps every layer of the shipped configs.
+ * The 3xTF32 plans are selected with `ups | 2` (conv) and `pad | 256` (wgrad). */
 int mk_conv2d_tc_plan(int N, int Hin, int Win, int Cin_p, int ups, int R, int S, int pad, int act, int Cout_p, int ldy,
                       int* out);
 int mk_conv2d_wgrad_tc_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int R, int S, int pad, int* out);
@@ -112,6 +122,9 @@ int mk_conv2d_wgrad(const float* x, int N, int Hin, int Win, int Cin_p, int ldx,
  * layout as mk_conv2d_wgrad.  Channel counts must be multiples of 4; returns -2 otherwise. */
 int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
                        int ldy, int R, int S, int pad, float* dwpack, void* stream);
+/* 3xTF32 variant (see mk_conv2d_tc_x3): both operand tiles are split hi + lo in shared memory. */
+int mk_conv2d_wgrad_tc_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
+                          int ldy, int R, int S, int pad, float* dwpack, void* stream);
 
 /* ---- normalisation: BatchNorm over (N,D,H,W) (sync_batchnorm/batchnorm.py:48-78 -> F.batch_norm semantics on the
  *      global batch) and InstanceNorm3d (discriminator.py:20) -------------------------------------------------

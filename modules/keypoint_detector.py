@@ -59,5 +59,9 @@ class KPDetector(nn.Module):
     def forward(self, x):
         b, _, d = x.shape[:3]
         a = ops.to_nhwc(x, _step(self.scale_factor))
-        logits = self.predictor.run(a)
+        if ops.KP_PRECISE:
+            with ops.reference_precision():   # bit-exact keypoint pixel indices need fp32-accurate convolutions
+                logits = self.predictor.run(a)
+        else:
+            logits = self.predictor.run(a)
         return ops.kp_head(logits, b, d, self.num_kp, self.temperature, self.kp_variance, self.clip_variance)

@@ -396,7 +396,10 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (bias_p && i < Cout_p) bias_p[i] = (bias && i < Co) ? bias[i] : 0.f;
     if (i >= total) return;
-    // modes 2/3 = modes 0/1 in the tensor-core layout [tap][Kout][Kin] (K-major rows), values rounded to TF32
+    // modes 2/3 = modes 0/1 in the tensor-core layout [tap][Kout][Kin] (K-major rows), values rounded to TF32;
+    // bit 3 (mode | 8): 3xTF32 pack - the TF32 remainder lo = rna(v - hi) follows the hi half at offset `total`
+    const int x3 = (mode >> 3) & 1;
+    mode &= 7;
     const int tc = mode >> 1;
     mode &= 1;
     const int Kin = mode == 0 ? Cin_p : Cout_p, Kout = mode == 0 ? Cout_p : Cin_p;
@@ -426,7 +429,12 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
     if (tc) {
         uint32_t u;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-        v = __uint_as_float(u);
+        const float hi = __uint_as_float(u);
+        if (x3) {
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - hi));
+            wp[total + i] = __uint_as_float(u);
+        }
+        v = hi;
     }
     wp[i] = v;
 }
@@ -436,7 +444,7 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
 //   py = 0: rows {0} | {1,2}      py = 1: rows {0,1} | {2}        (same for columns)
 // Layout [parity = py*2+px][tap = r2*2+s2][Cout_p][Cin_p], rounded to TF32 after the sum.
 __global__ void k_pack_weight_ups(const float* __restrict__ w, int Co, int Ci, const int* __restrict__ cin_map,
-                                  int Cin_p, int Cout_p, float* __restrict__ wp, long long total) {
+                                  int Cin_p, int Cout_p, float* __restrict__ wp, long long total, int x3) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int ci_p = (int)(i % Cin_p);
@@ -456,7 +464,12 @@ __global__ void k_pack_weight_ups(const float* __restrict__ w, int Co, int Ci, c
     }
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    wp[i] = __uint_as_float(u);
+    const float hi = __uint_as_float(u);
+    wp[i] = hi;
+    if (x3) {
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - hi));
+        wp[total + i] = __uint_as_float(u);
+    }
 }
 
 MK_EXPORT int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int groups, const int* cin_map,
@@ -465,11 +478,11 @@ MK_EXPORT int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int 
     long long total = (long long)R * S * Cin_p * Cout_p;
     if (total == 0) return 0;
     MK_REQUIRE(total >= Cout_p, "mk_pack_weight: degenerate shape");
-    if (mode == 4) {
+    if ((mode & 7) == 4) {
         MK_REQUIRE(R == 3 && S == 3 && groups == 1, "mk_pack_weight mode 4: 3x3 ungrouped kernels only");
         total = 16LL * Cin_p * Cout_p;
         k_pack_weight_ups<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Co, Cig, cin_map, Cin_p,
-                                                                                           Cout_p, wpack, total);
+                                                                                           Cout_p, wpack, total, mode >> 3);
         if (bias_p)  // zero-padded bias copy: the regular kernel with an empty weight range (total = 0)
             k_pack_weight<<<(unsigned)mk_cdiv(Cout_p, 256), 256, 0, (cudaStream_t)stream>>>(
                 w, Co, Cig, R, S, groups, cin_map, Cin_p, Cout_p, 0, wpack, 0, bias, bias_p);

@@ -18,6 +18,12 @@
 // * split-K (grid.z): layers whose tile count cannot fill 148 SMs (deep, low-resolution levels: 128 pixels x 1152 K)
 //   split the (tap, channel-chunk) loop over several CTAs that combine with red.global.add.v4.f32 into the
 //   zero-initialised output; split 0 carries the bias / residual.  Only for the linear epilogue (act == 0).
+// * 3xTF32 (mk_conv2d_tc_x3, "reference precision"): every fp32 operand is split hi + lo with hi = rna_tf32(v),
+//   lo = rna_tf32(v - hi) and the product is accumulated as A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same TMEM
+//   accumulator (the dropped lo*lo term is 2^-22 relative).  The weight pack carries its lo half behind the hi half
+//   (mk_pack_weight mode | 8); the ACTIVATION tile is split in shared memory by the four epilogue warps, idle during
+//   the main loop: hi written in place, lo into a second tile of the same swizzled layout (an elementwise map keeps
+//   the layout), published to the tensor core's async proxy with fence.proxy.async + a per-stage mbarrier.
 // Same contract as mk_conv2d (conv.cu) for stride-1 convs without the pool option.
 #include "common.cuh"
 #include "../../include/monkey_b200.h"
@@ -40,6 +46,7 @@ struct TcP {
     int TW, TH, TN, tilesW, tilesH;
     int nstages, stage_bytes;  // smem ring: stage = A tile (16 KB) + B tile (b_rows x 128 B)
     int ksplit, iters_per_split, tmem_cols;
+    int x3, b_bytes, lo_tap_offset;  // 3xTF32: stage = A | B_hi | A_lo | B_lo ; lo weights at tap + lo_tap_offset
     const float* scale; const float* shift; const float* resid; int ldr, act; float slope;
     float* y;
 };
@@ -51,7 +58,8 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
     const int STAGES = p.nstages, STAGE_BYTES = p.stage_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty = full + MAX_STAGES;
-    uint64_t* tmem_full = empty + MAX_STAGES;
+    uint64_t* splitb = empty + MAX_STAGES;
+    uint64_t* tmem_full = splitb + MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,7 +86,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&splitb[s], 4); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -104,9 +112,12 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                 const int r = tap / p.S, s = tap - r * p.S;
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* a = smem + stage * STAGE_BYTES;
-                mbar_expect_tx(&full[stage], STAGE_BYTES);
+                mbar_expect_tx(&full[stage], A_BYTES + (p.x3 ? 2 : 1) * p.b_bytes);
                 tma_load_4d(a, &tmA, &full[stage], ch * KC, w0 + s - pad_w, h0 + r - pad_h, n0);
                 tma_load_3d(a + A_BYTES, &tmB, &full[stage], ch * KC, cout0, tap0 + tap);
+                if (p.x3)
+                    tma_load_3d(a + 2 * A_BYTES + p.b_bytes, &tmB, &full[stage], ch * KC, cout0,
+                                p.lo_tap_offset + tap0 + tap);
             }
         }
     } else if (warp == 1) {
@@ -116,7 +127,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             const int stage = li % STAGES;
             const uint32_t phase = (li / STAGES) & 1;
             const int ch = (it0 + li) % nchunks;
-            mbar_wait(&full[stage], phase);
+            mbar_wait(p.x3 ? &splitb[stage] : &full[stage], phase);  // x3: the split tile implies the landed one
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const uint8_t* a = smem + stage * STAGE_BYTES;
@@ -124,6 +135,15 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                 int kleft = p.Cin_p - ch * KC;
                 if (kleft > KC) kleft = KC;
                 const int nk = (kleft + 7) >> 3;  // UMMA K = 8 tf32 (32 bytes); the TMA zero-fills the ragged tail
+                if (p.x3) {
+                    const uint64_t aldesc = umma_desc(a + A_BYTES + p.b_bytes);
+                    const uint64_t bldesc = umma_desc(a + 2 * A_BYTES + p.b_bytes);
+                    for (int k = 0; k < nk; ++k) {   // small terms first, then the hi*hi product
+                        umma_tf32(tmem_base, aldesc + 2 * k, bdesc + 2 * k, idesc, (li | k) ? 1u : 0u);
+                        umma_tf32(tmem_base, adesc + 2 * k, bldesc + 2 * k, idesc, 1u);
+                        umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                    }
+                } else
                 for (int k = 0; k < nk; ++k)      // advancing 32 B inside the 128 B swizzle row = +2 in 16 B units
                     umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (li | k) ? 1u : 0u);
                 umma_commit(&empty[stage]);       // frees the smem stage when these MMAs retire
@@ -132,7 +152,27 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             __syncwarp();
         }
     } else if (warp >= 4) {
-        // ===================================================================== epilogue
+        // ===================================================================== 3xTF32 operand split, then epilogue
+        if (p.x3) {
+            const int tid = threadIdx.x - 128;
+            for (int li = 0; li < niter; ++li) {
+                const int stage = li % STAGES;
+                mbar_wait(&full[stage], (li / STAGES) & 1);
+                float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + A_BYTES + p.b_bytes);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+                    float4 v = hi[tid + 128 * i], h, l;
+                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                    hi[tid + 128 * i] = h;
+                    lo[tid + 128 * i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&splitb[stage]);
+            }
+        }
         const int q = warp & 3;               // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;        // GEMM row = pixel of the tile, TMA box order (w fastest, then h, n)
         const int iw = row % p.TW;
@@ -188,6 +228,7 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
 }  // namespace
 
 static thread_local int* t_plan_out = nullptr;  // set by mk_conv2d_tc_plan for a dry run
+static thread_local int t_x3 = 0;               // set by mk_conv2d_tc_x3 around its call of mk_conv2d_tc
 
 // Returns 0 on success, -2 if the shape is outside this kernel's envelope (caller uses mk_conv2d instead).
 MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
@@ -217,7 +258,10 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     p.scale = scale; p.shift = shift; p.resid = resid; p.ldr = ldr; p.act = act; p.slope = slope; p.y = y;
 
     const int b_rows = Cout_p < BN_MAX ? (Cout_p + 15) & ~15 : BN_MAX;  // weight rows per stage = UMMA N
-    p.stage_bytes = A_BYTES + b_rows * KC * 4;
+    p.x3 = t_x3;
+    p.b_bytes = b_rows * KC * 4;
+    p.lo_tap_offset = R * S * (p.ups ? 4 : 1);
+    p.stage_bytes = (p.x3 ? 2 : 1) * (A_BYTES + p.b_bytes);
     p.tmem_cols = b_rows <= 32 ? 32 : (b_rows <= 64 ? 64 : 128);
     const int grid_y = (Cout_p + BN_MAX - 1) / BN_MAX;
     const long long tiles = (long long)p.tilesW * p.tilesH * tilesN * grid_y * (p.ups ? 4 : 1);
@@ -265,7 +309,7 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
         MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc: activation tensor map rejected (%d)", (int)r);
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S * (p.ups ? 4 : 1))};
+        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S * (p.ups ? 4 : 1) * (p.x3 ? 2 : 1))};
         cuuint64_t strides[2] = {(cuuint64_t)Cin_p * 4, (cuuint64_t)Cin_p * Cout_p * 4};
         cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)b_rows, 1};
         cuuint32_t es[3] = {1, 1, 1};
@@ -290,6 +334,19 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     return mk_check_launch("mk_conv2d_tc");
 }
 
+// 3xTF32 variant (fp32-accurate tensor-core convolution): same contract, `wpack_tc` packed with mode | 8 (hi half
+// followed by the lo half).
+MK_EXPORT int mk_conv2d_tc_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
+                              const float* wpack_tc, int R, int S, int pad, const float* scale, const float* shift,
+                              const float* resid, int ldr, int act, float slope, float* y, int Cout_p, int ldy,
+                              void* stream) {
+    t_x3 = 1;
+    const int rc = mk_conv2d_tc(x, N, Hin, Win, Cin_p, ldx, ups, wpack_tc, R, S, pad, scale, shift, resid, ldr, act, slope,
+                                y, Cout_p, ldy, stream);
+    t_x3 = 0;
+    return rc;
+}
+
 // Dry run of mk_conv2d_tc's host-side planning (no device state touched, works without a GPU: 148 SMs assumed):
 // out[16] = grid.x, grid.y, grid.z, dynamic smem bytes, ring stages, ksplit, K iterations per split, K iterations,
 // TMEM columns, TMA box TW, TH, TN, weight rows per stage, stage bytes, Ho, Wo.  tests/test_tc_plans.py sweeps every
@@ -297,6 +354,9 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
 MK_EXPORT int mk_conv2d_tc_plan(int N, int Hin, int Win, int Cin_p, int ups, int R, int S, int pad, int act, int Cout_p,
                                 int ldy, int* out) {
     MK_REQUIRE(out != nullptr, "mk_conv2d_tc_plan: out is NULL");
+    t_x3 = ups >> 1;  // bit 1 of `ups` selects the 3xTF32 plan
+    ups &= 1;
+    struct Reset { ~Reset() { t_x3 = 0; } } reset;
     t_plan_out = out;
     const int rc = mk_conv2d_tc(nullptr, N, Hin, Win, Cin_p, Cin_p, ups, nullptr, R, S, pad, nullptr, nullptr, nullptr, 0,
                                 act, 0.f, nullptr, Cout_p, ldy, nullptr);

@@ -27,6 +27,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (!done && ++spins > (1u << 26)) __trap();  // a protocol bug must abort, never hang the GPU box
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 3xTF32 operand split: hi = rna_tf32(v) (low 13 mantissa bits zero, exact whatever the tensor core does with them),
+// lo = rna_tf32(v - hi); v - hi is exact in fp32, so hi + lo == v to 2^-22 relative
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    hi = __uint_as_float(h);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
+    lo = __uint_as_float(l);
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

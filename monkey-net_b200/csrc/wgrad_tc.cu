@@ -14,6 +14,9 @@
 //     layers (24 -> 24 @ 64x64 x 32 frames) took 150 us; now they are a single pass over X and dY.
 //   * only the 32-channel boxes that exist are staged (ceil(co/32) A boxes, ceil(ci/32) B boxes).  The MMA still runs
 //     M = 128: accumulator rows beyond the staged boxes are products of stale shared memory and are never read.
+//   * 3xTF32 (mk_conv2d_wgrad_tc_x3): both operands are activations, so both rings carry a lo half behind the hi half
+//     of every slot; the four epilogue warps split each landed slot in shared memory (hi in place, lo = rna(v - hi),
+//     same swizzled layout) and publish it through a_split / b_split mbarriers; the issuer runs lo*hi + hi*lo + hi*hi.
 //   * grid = (co tiles, tap groups x ci tiles, pixel splits); splits combine with fp32 atomics (red) into the packed
 //     gradient, whose layout [tap][Cin_p][Cout_p] makes the epilogue's per-column writes coalesced across lanes.
 #include "tc_common.cuh"
@@ -32,6 +35,7 @@ struct WgTcP {
     int TW, TH, TN, tilesW, tilesH, nchunks, chunks_per_split, n_ci_tiles;
     int taps_per_cta, n_tap_groups, npad;   // npad = accumulator columns per tap (round16 of the ci tile)
     int na_max, nb_max, a_slots, b_slots, tmem_cols;
+    int x3;   // 3xTF32: slot = [hi boxes | lo boxes]
     float* dw;
 };
 
@@ -49,14 +53,17 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
                                                   const __grid_constant__ CUtensorMap tmX, const WgTcP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int A_SLOT = p.na_max * BOX_BYTES, B_SLOT = p.nb_max * BOX_BYTES;
+    const int A_HALF = p.na_max * BOX_BYTES, B_HALF = p.nb_max * BOX_BYTES;
+    const int A_SLOT = A_HALF << p.x3, B_SLOT = B_HALF << p.x3;
     uint8_t* a_ring = smem;
     uint8_t* b_ring = smem + p.a_slots * A_SLOT;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(b_ring + p.b_slots * B_SLOT);
     uint64_t* a_empty = a_full + MAX_A;
     uint64_t* b_full = a_empty + MAX_A;
     uint64_t* b_empty = b_full + MAX_B;
-    uint64_t* tmem_full = b_empty + MAX_B;
+    uint64_t* a_split = b_empty + MAX_B;
+    uint64_t* b_split = a_split + MAX_A;
+    uint64_t* tmem_full = b_split + MAX_B;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,8 +83,8 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < MAX_A; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < MAX_B; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < MAX_A; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_split[i], 4); }
+        for (int i = 0; i < MAX_B; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&b_split[i], 4); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -126,15 +133,25 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
         int bi = 0;
         for (int qi = 0; qi < nq; ++qi) {
             const int as = qi % p.a_slots;
-            mbar_wait(&a_full[as], (qi / p.a_slots) & 1);
+            mbar_wait(p.x3 ? &a_split[as] : &a_full[as], (qi / p.a_slots) & 1);
             for (int t = 0; t < ntaps; ++t, ++bi) {
                 const int bs = bi % p.b_slots;
-                mbar_wait(&b_full[bs], (bi / p.b_slots) & 1);
+                mbar_wait(p.x3 ? &b_split[bs] : &b_full[bs], (bi / p.b_slots) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint64_t adesc = umma_desc_mn(a_ring + as * A_SLOT);
                     const uint64_t bdesc = umma_desc_mn(b_ring + bs * B_SLOT);
                     const uint32_t dcol = tmem_base + (uint32_t)(t * p.npad);
+                    if (p.x3) {
+                        const uint64_t aldesc = umma_desc_mn(a_ring + as * A_SLOT + A_HALF);
+                        const uint64_t bldesc = umma_desc_mn(b_ring + bs * B_SLOT + B_HALF);
+#pragma unroll
+                        for (int k = 0; k < PC / 8; ++k) {
+                            umma_tf32(dcol, aldesc + 64 * k, bdesc + 64 * k, idesc, (qi | k) ? 1u : 0u);
+                            umma_tf32(dcol, adesc + 64 * k, bldesc + 64 * k, idesc, 1u);
+                            umma_tf32(dcol, adesc + 64 * k, bdesc + 64 * k, idesc, 1u);
+                        }
+                    } else
 #pragma unroll
                     for (int k = 0; k < PC / 8; ++k)  // 8 pixel rows = 1024 B = 64 sixteen-byte units
                         umma_tf32(dcol, adesc + 64 * k, bdesc + 64 * k, idesc, (qi | k) ? 1u : 0u);
@@ -148,7 +165,37 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
             }
         }
     } else if (warp >= 4 && nq > 0) {
-        // ===================================================================== epilogue
+        // ===================================================================== 3xTF32 operand split, then epilogue
+        if (p.x3) {
+            const int tid = threadIdx.x - 128;
+            auto split_slot = [&](uint8_t* slot, int nboxes, int half) {
+                float4* hi = reinterpret_cast<float4*>(slot);
+                float4* lo = reinterpret_cast<float4*>(slot + half);
+                const int n4 = nboxes * (BOX_BYTES / 16);
+                for (int i = tid; i < n4; i += 128) {
+                    float4 v = hi[i], h, l;
+                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                    hi[i] = h;
+                    lo[i] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+            };
+            int bi = 0;
+            for (int qi = 0; qi < nq; ++qi) {
+                const int as = qi % p.a_slots;
+                mbar_wait(&a_full[as], (qi / p.a_slots) & 1);
+                split_slot(a_ring + as * A_SLOT, na, A_HALF);
+                if (lane == 0) mbar_arrive(&a_split[as]);
+                for (int t = 0; t < ntaps; ++t, ++bi) {
+                    const int bs = bi % p.b_slots;
+                    mbar_wait(&b_full[bs], (bi / p.b_slots) & 1);
+                    split_slot(b_ring + bs * B_SLOT, nb, B_HALF);
+                    if (lane == 0) mbar_arrive(&b_split[bs]);
+                }
+            }
+        }
         const int q = warp & 3;
         const int co = co0 + q * 32 + lane;
         const bool valid = co < p.Cout_p;
@@ -181,6 +228,7 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
 }  // namespace
 
 static thread_local int* t_wplan_out = nullptr;  // set by mk_conv2d_wgrad_tc_plan for a dry run
+static thread_local int t_wx3 = 0;               // set by mk_conv2d_wgrad_tc_x3
 
 MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,
                                  int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream) {
@@ -220,8 +268,9 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
     p.chunks_per_split = (int)mk_cdiv(p.nchunks, splits);
     splits = mk_cdiv(p.nchunks, p.chunks_per_split);
     // rings: never deeper than the loops; within ~100 KB when two CTAs can share an SM, ~200 KB otherwise
-    const int budget = (p.tmem_cols <= 256 && tiles * splits > sms) ? 100 * 1024 : 200 * 1024;
-    const int a_slot = p.na_max * BOX_BYTES, b_slot = p.nb_max * BOX_BYTES;
+    p.x3 = t_wx3;
+    const int budget = (p.tmem_cols <= 256 && tiles * splits > sms && !p.x3) ? 100 * 1024 : 200 * 1024;
+    const int a_slot = (p.na_max * BOX_BYTES) << p.x3, b_slot = (p.nb_max * BOX_BYTES) << p.x3;
     p.a_slots = p.chunks_per_split < 2 ? 1 : 2;
     int bs = (budget - p.a_slots * a_slot) / b_slot;
     const long long b_loads = (long long)p.chunks_per_split * p.taps_per_cta;
@@ -232,7 +281,7 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
     // the M = 128 MMA reads four 32-channel A boxes whatever Cout is: the rows beyond the staged boxes are never
     // used, but the addresses must lie inside this CTA's shared-memory allocation
     int ring_bytes = p.a_slots * a_slot + p.b_slots * b_slot + 512 /*barriers*/;
-    const int a_reach = (p.a_slots - 1) * a_slot + 4 * BOX_BYTES;
+    const int a_reach = (p.a_slots - 1) * a_slot + (p.x3 ? p.na_max * BOX_BYTES : 0) + 4 * BOX_BYTES;
     if (ring_bytes < a_reach) ring_bytes = a_reach;
     const int smem_bytes = ring_bytes + 1024 /*align*/;
     MK_REQUIRE(smem_bytes <= WSMEM_MAX, "mk_conv2d_wgrad_tc: shared memory plan exceeds 227 KB (%d)", smem_bytes);
@@ -282,11 +331,23 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
     return mk_check_launch("mk_conv2d_wgrad_tc");
 }
 
+// 3xTF32 variant: fp32-accurate weight gradient on the tensor cores (same contract).
+MK_EXPORT int mk_conv2d_wgrad_tc_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,
+                                    int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream) {
+    t_wx3 = 1;
+    const int rc = mk_conv2d_wgrad_tc(x, N, Hin, Win, Cin_p, ldx, dy, Cout_p, ldy, R, S, pad, dwpack, stream);
+    t_wx3 = 0;
+    return rc;
+}
+
 // Dry run of mk_conv2d_wgrad_tc's host-side planning (see mk_conv2d_tc_plan): out[16] = grid.x (co tiles), grid.y
 // (tap groups x ci tiles), grid.z (pixel splits), dynamic smem bytes, A ring slots, B ring slots, taps per CTA,
 // accumulator columns per tap, TMEM columns, TMA box TW, TH, TN, pixel chunks, chunks per split, A boxes, B boxes.
 MK_EXPORT int mk_conv2d_wgrad_tc_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int R, int S, int pad, int* out) {
     MK_REQUIRE(out != nullptr, "mk_conv2d_wgrad_tc_plan: out is NULL");
+    t_wx3 = pad >> 8;  // bits 8+ of `pad` select the 3xTF32 plan
+    pad &= 255;
+    struct Reset { ~Reset() { t_wx3 = 0; } } reset;
     t_wplan_out = out;
     const int rc = mk_conv2d_wgrad_tc(nullptr, N, Hin, Win, Cin_p, Cin_p, nullptr, Cout_p, Cout_p, R, S, pad, nullptr,
                                       nullptr);

@@ -174,3 +174,39 @@ def golden_weights(gold, tag):
     import torch
     pre = 'w/%s/' % tag
     return {k[len(pre):]: torch.from_numpy(gold[k].copy()) for k in gold.files if k.startswith(pre)}
+
+
+# ----------------------------------------------------------------------------------------------- reference drivers
+class TinyPairs(torch.utils.data.Dataset):
+    """What the reference's FramesDataset hands to train.py:99,109 - dicts of (C,D,H,W) float tensors in [0,1]
+    ('source' and 'video', D = 1) - from seeded smooth frames instead of files (data loading is out of scope)."""
+
+    def __init__(self, n=4, res=32, seed=30):
+        self.src = smooth_frames(n, 1, res, seed)
+        self.vid = smooth_frames(n, 1, res, seed + 1)
+
+    def __len__(self):
+        return self.src.shape[0]
+
+    def __getitem__(self, i):
+        return {'source': self.src[i], 'video': self.vid[i]}
+
+
+def driver_config(num_epochs=2):
+    """tiny_config() with the train_params the reference's train() reads (train.py:79-107)."""
+    cfg = tiny_config()
+    tp = cfg['train_params']
+    tp['num_epochs'], tp['epoch_milestones'], tp['batch_size'] = num_epochs, [1], 2
+    tp['log_params'] = {}
+    cfg['visualizer_params'] = {}
+    return cfg
+
+
+def run_reference_train(train_mod, nets, cfg, device_ids, seed=1234):
+    """Call the reference's own train() (train.py:78-155, imported unchanged by oracle/ref_shim.load_driver) and
+    return the per-iteration loss records its Logger received."""
+    from oracle import ref_shim
+    gen, disc, kp = nets
+    torch.manual_seed(seed)   # DataLoader(shuffle=True) draws its permutation seed from the global generator
+    train_mod.train(cfg, gen, disc, kp, None, '/tmp/mk_unused_log_dir', TinyPairs(), device_ids)
+    return ref_shim._RecordingLogger.records

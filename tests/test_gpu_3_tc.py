@@ -1,6 +1,6 @@
-"""Tensor-core (tcgen05 / TMA, TF32) convolution: kernel-level parity against the exact fp32 kernel on the same
-device buffers, and module-level parity of the whole generator in 'tf32' conv mode against the CPU oracle.
-TF32 keeps 10 mantissa bits, so kernel tolerances are relative 2e-3 (of the output's max-abs)."""
+"""Tensor-core (tcgen05 / TMA) convolution kernels - 1xTF32, 3xTF32 - and the exact FFMA kernels: kernel-level parity
+against torch's F.conv2d / autograd in double precision on the same device buffers, and module-level parity of the
+whole generator in the tensor-core modes against the CPU oracle."""
 import pytest
 import torch
 
@@ -33,77 +33,108 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('cin,cout,k,pad,H,W,N,resid,act', CASES)
-def test_conv_tc_matches_fp32_kernel(cin, cout, k, pad, H, W, N, resid, act):
+# Every kernel is compared with torch's own convolution evaluated in DOUBLE precision on the same device buffers
+# (F.conv2d + autograd, the op the reference calls) - not with another kernel of this repository.  Tolerances are
+# relative to the output's max-abs: TF32 keeps 10 mantissa bits (2e-3), 3xTF32 and the FFMA kernel are fp32-accurate.
+KERNEL_TOL = {'tf32': 2e-3, 'tf32x3': 2e-5, 'ffma': 1e-5}
+
+
+def _torch_conv(x, w, b, pad, r, act, ups=False):
+    """NHWC fp32 inputs -> NHWC double reference of act(conv2d(x) + b + r)"""
+    xd = x.double().permute(0, 3, 1, 2)
+    if ups:
+        xd = torch.nn.functional.interpolate(xd, scale_factor=2, mode='nearest')
+    y = torch.nn.functional.conv2d(xd, w[:, :, 0].double(), b.double() if b is not None else None, padding=pad)
+    y = y.permute(0, 2, 3, 1)
+    if r is not None:
+        y = y + r.double()
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = torch.sigmoid(y)
+    return y
+
+
+def _run_conv_kernel(kernel, x, w, b, k, pad, r, act, ups=0):
     from monkey_net_b200 import lib
+    dev = x.device
+    st = torch.cuda.current_stream().cuda_stream
+    N, H, W, cin = x.shape
+    cout = w.shape[0]
+    Hl, Wl = H << ups, W << ups
+    Ho, Wo = Hl + 2 * pad - k + 1, Wl + 2 * pad - k + 1
+    x3 = kernel == 'tf32x3'
+    taps = (16 if ups else k * k) if kernel != 'ffma' else k * k
+    wp = torch.empty(taps * cin * cout * (2 if x3 else 1), device=dev)
+    bp = torch.empty(cout, device=dev)
+    mode = 0 if kernel == 'ffma' else ((4 if ups else 2) | (8 if x3 else 0))
+    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, mode, wp.data_ptr(),
+             b.data_ptr() if b is not None else None, bp.data_ptr() if b is not None else None, st)
+    y = torch.full((N, Ho, Wo, cout), float('nan'), device=dev)
+    rp = r.data_ptr() if r is not None else None
+    bpp = bp.data_ptr() if b is not None else None
+    if kernel == 'ffma':
+        lib.call('mk_conv2d', x.data_ptr(), N, H, W, cin, cin, ups, wp.data_ptr(), k, k, pad, None, bpp, rp,
+                 cout if r is not None else 0, act, 0.0, y.data_ptr(), cout, cout, 0, st)
+    else:
+        lib.call('mk_conv2d_tc_x3' if x3 else 'mk_conv2d_tc', x.data_ptr(), N, H, W, cin, cin, ups, wp.data_ptr(), k, k,
+                 pad, None, bpp, rp, cout if r is not None else 0, act, 0.0, y.data_ptr(), cout, cout, st)
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize('kernel', ['tf32', 'tf32x3', 'ffma'])
+@pytest.mark.parametrize('cin,cout,k,pad,H,W,N,resid,act', CASES)
+def test_conv_kernels_match_torch_conv2d(cin, cout, k, pad, H, W, N, resid, act, kernel):
     torch.manual_seed(cin + cout + k)
     dev = torch.device('cuda')
-    st = torch.cuda.current_stream().cuda_stream
     x = torch.randn(N, H, W, cin, device=dev)
     w = torch.randn(cout, cin, 1, k, k, device=dev) / (cin * k * k) ** 0.5
     b = torch.randn(cout, device=dev)
     Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
     r = torch.randn(N, Ho, Wo, cout, device=dev) if resid else None
-    wp, wt = torch.empty(k * k * cin * cout, device=dev), torch.empty(k * k * cin * cout, device=dev)
-    bp = torch.empty(cout, device=dev)
-    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, 0, wp.data_ptr(), b.data_ptr(),
-             bp.data_ptr(), st)
-    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, 2, wt.data_ptr(), None, None, st)
-    y0 = torch.empty(N, Ho, Wo, cout, device=dev)
-    y1 = torch.full((N, Ho, Wo, cout), float('nan'), device=dev)
-    rp = r.data_ptr() if resid else None
-    lib.call('mk_conv2d', x.data_ptr(), N, H, W, cin, cin, 0, wp.data_ptr(), k, k, pad, None, bp.data_ptr(), rp,
-             cout if resid else 0, act, 0.0, y0.data_ptr(), cout, cout, 0, st)
-    lib.call('mk_conv2d_tc', x.data_ptr(), N, H, W, cin, cin, 0, wt.data_ptr(), k, k, pad, None, bp.data_ptr(), rp,
-             cout if resid else 0, act, 0.0, y1.data_ptr(), cout, cout, st)
-    torch.cuda.synchronize()
-    assert not torch.isnan(y1).any(), 'tensor-core kernel left outputs unwritten'
-    err = float((y0 - y1).abs().max()) / (float(y0.abs().max()) + 1e-12)
-    assert err < 2e-3, err
+    y = _run_conv_kernel(kernel, x, w, b, k, pad, r, act)
+    assert not torch.isnan(y).any(), 'kernel left outputs unwritten'
+    ref = _torch_conv(x, w, b, pad, r, act)
+    err = float((y.double() - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+    assert err < KERNEL_TOL[kernel], err
 
 
+@pytest.mark.parametrize('kernel', ['tf32', 'tf32x3', 'ffma'])
 @pytest.mark.parametrize('cin,cout,H,W,N', [(64, 32, 16, 16, 2), (128, 64, 4, 4, 4), (40, 16, 9, 5, 3), (256, 128, 2, 2, 8)])
-def test_conv_tc_upsampled_subpixel(cin, cout, H, W, N):
-    """conv3x3(nearest_x2(x)) as four 2x2 sub-pixel convs on tensor cores == the fp32 kernel's on-the-fly upsample."""
-    from monkey_net_b200 import lib
+def test_conv_upsampled_matches_torch(cin, cout, H, W, N, kernel):
+    """conv3x3(nearest_x2(x)) (util.py:84-85): four 2x2 sub-pixel convs on tensor cores / on-the-fly upsample in the
+    FFMA kernel == F.interpolate + F.conv2d."""
     torch.manual_seed(cin + H)
     dev = torch.device('cuda')
-    st = torch.cuda.current_stream().cuda_stream
     x = torch.randn(N, H, W, cin, device=dev)
     w = torch.randn(cout, cin, 1, 3, 3, device=dev) / (cin * 9) ** 0.5
     b = torch.randn(cout, device=dev)
-    wp, wt = torch.empty(9 * cin * cout, device=dev), torch.empty(16 * cin * cout, device=dev)
-    bp, bp2 = torch.empty(cout, device=dev), torch.empty(cout, device=dev)
-    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, 3, 3, 1, None, cin, cout, 0, wp.data_ptr(), b.data_ptr(),
-             bp.data_ptr(), st)
-    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, 3, 3, 1, None, cin, cout, 4, wt.data_ptr(), b.data_ptr(),
-             bp2.data_ptr(), st)
-    y0 = torch.empty(N, 2 * H, 2 * W, cout, device=dev)
-    y1 = torch.full((N, 2 * H, 2 * W, cout), float('nan'), device=dev)
-    lib.call('mk_conv2d', x.data_ptr(), N, H, W, cin, cin, 1, wp.data_ptr(), 3, 3, 1, None, bp.data_ptr(), None, 0, 0,
-             0.0, y0.data_ptr(), cout, cout, 0, st)
-    lib.call('mk_conv2d_tc', x.data_ptr(), N, H, W, cin, cin, 1, wt.data_ptr(), 3, 3, 1, None, bp2.data_ptr(), None, 0,
-             0, 0.0, y1.data_ptr(), cout, cout, st)
-    torch.cuda.synchronize()
-    assert torch.equal(bp, bp2)
-    assert not torch.isnan(y1).any()
-    err = float((y0 - y1).abs().max()) / (float(y0.abs().max()) + 1e-12)
-    assert err < 2e-3, err
+    y = _run_conv_kernel(kernel, x, w, b, 3, 1, None, 0, ups=1)
+    assert not torch.isnan(y).any()
+    ref = _torch_conv(x, w, b, 1, None, 0, ups=True)
+    err = float((y.double() - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+    # the sub-pixel pack pre-sums up to four taps before the TF32 rounding: same order of error
+    assert err < KERNEL_TOL[kernel] * (2 if kernel == 'tf32x3' else 1), err
 
 
-@pytest.mark.parametrize('cin,cout,k,pad,H,W,N', [(32, 64, 3, 1, 16, 16, 4), (64, 128, 3, 1, 32, 32, 2),
-                                                   (16, 32, 3, 1, 64, 64, 2), (48, 144, 3, 1, 13, 9, 3),
-                                                   (256, 256, 3, 1, 4, 4, 8), (512, 128, 3, 1, 2, 2, 32),
-                                                   (64, 128, 4, 0, 29, 29, 2), (48, 16, 1, 0, 16, 16, 2),
-                                                   (160, 32, 3, 1, 8, 8, 4), (4, 32, 3, 1, 32, 32, 2),
-                                                   (24, 24, 3, 1, 16, 16, 2), (132, 128, 3, 1, 8, 8, 2),
-                                                   (36, 8, 3, 1, 16, 16, 2),
-                                                   (24, 24, 3, 1, 64, 64, 8),     # many chunks per CTA: both rings wrap
-                                                   (4, 32, 4, 0, 64, 64, 2),      # discriminator block 0: 16 taps x 16 cols
-                                                   (32, 64, 4, 0, 31, 31, 2),     # 16 taps x 32 cols = all 512 TMEM columns
-                                                   (128, 128, 3, 1, 2, 2, 3),     # TMA box larger than the batch (TN > N)
-                                                   (300, 40, 1, 0, 7, 7, 5)])     # 1x1, three ci tiles (128+128+44)
-def test_wgrad_tc_matches_fp32_kernel(cin, cout, k, pad, H, W, N):
+WGRAD_CASES = [(32, 64, 3, 1, 16, 16, 4), (64, 128, 3, 1, 32, 32, 2),
+               (16, 32, 3, 1, 64, 64, 2), (48, 144, 3, 1, 13, 9, 3),
+               (256, 256, 3, 1, 4, 4, 8), (512, 128, 3, 1, 2, 2, 32),
+               (64, 128, 4, 0, 29, 29, 2), (48, 16, 1, 0, 16, 16, 2),
+               (160, 32, 3, 1, 8, 8, 4), (4, 32, 3, 1, 32, 32, 2),
+               (24, 24, 3, 1, 16, 16, 2), (132, 128, 3, 1, 8, 8, 2),
+               (36, 8, 3, 1, 16, 16, 2),
+               (24, 24, 3, 1, 64, 64, 8),     # many chunks per CTA: both rings wrap
+               (4, 32, 4, 0, 64, 64, 2),      # discriminator block 0: 16 taps x 16 cols
+               (32, 64, 4, 0, 31, 31, 2),     # 16 taps x 32 cols = all 512 TMEM columns
+               (128, 128, 3, 1, 2, 2, 3),     # TMA box larger than the batch (TN > N)
+               (300, 40, 1, 0, 7, 7, 5)]      # 1x1, three ci tiles (128+128+44)
+
+
+@pytest.mark.parametrize('kernel', ['tf32', 'tf32x3', 'ffma'])
+@pytest.mark.parametrize('cin,cout,k,pad,H,W,N', WGRAD_CASES)
+def test_wgrad_kernels_match_torch_autograd(cin, cout, k, pad, H, W, N, kernel):
     from monkey_net_b200 import lib
     torch.manual_seed(cin + cout)
     dev = torch.device('cuda')
@@ -111,14 +142,20 @@ def test_wgrad_tc_matches_fp32_kernel(cin, cout, k, pad, H, W, N):
     Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
     x = torch.randn(N, H, W, cin, device=dev)
     dy = torch.randn(N, Ho, Wo, cout, device=dev)
-    d0 = torch.empty(k * k * cin * cout, device=dev)
-    d1 = torch.full((k * k * cin * cout,), float('nan'), device=dev)
-    lib.call('mk_conv2d_wgrad', x.data_ptr(), N, H, W, cin, cin, 0, dy.data_ptr(), cout, cout, k, k, pad, d0.data_ptr(), st)
-    lib.call('mk_conv2d_wgrad_tc', x.data_ptr(), N, H, W, cin, cin, dy.data_ptr(), cout, cout, k, k, pad, d1.data_ptr(), st)
+    d = torch.full((k * k * cin * cout,), float('nan'), device=dev)
+    if kernel == 'ffma':
+        lib.call('mk_conv2d_wgrad', x.data_ptr(), N, H, W, cin, cin, 0, dy.data_ptr(), cout, cout, k, k, pad, d.data_ptr(), st)
+    else:
+        lib.call('mk_conv2d_wgrad_tc_x3' if kernel == 'tf32x3' else 'mk_conv2d_wgrad_tc', x.data_ptr(), N, H, W, cin, cin,
+                 dy.data_ptr(), cout, cout, k, k, pad, d.data_ptr(), st)
     torch.cuda.synchronize()
-    assert not torch.isnan(d1).any()
-    err = float((d0 - d1).abs().max()) / (float(d0.abs().max()) + 1e-12)
-    assert err < 2e-3, err
+    assert not torch.isnan(d).any()
+    wz = torch.zeros(cout, cin, k, k, device=dev, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), wz, None, padding=pad)
+    (gw,) = torch.autograd.grad(y, wz, dy.double().permute(0, 3, 1, 2))
+    ref = gw.permute(2, 3, 1, 0).reshape(-1)          # (Co,Ci,R,S) -> [tap][Ci][Co]
+    err = float((d.double() - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+    assert err < KERNEL_TOL[kernel] * (2 if kernel == 'tf32x3' else 1), err
 
 
 def test_train_step_tf32_mode_gradients():
