@@ -106,13 +106,23 @@ int mk_conv2d_tc_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx,
 int mk_conv2d_tc_plan(int N, int Hin, int Win, int Cin_p, int ups, int R, int S, int pad, int act, int Cout_p, int ldy,
                       int* out);
 int mk_conv2d_wgrad_tc_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int R, int S, int pad, int* out);
-/* EXPERIMENTAL, opt-in (MONKEY_B200_CONV_HALO=1), not yet validated on hardware: same contract as mk_conv2d_tc for
- * stride-1 3x3 / 4x4 convolutions without upsample on maps of at least 8 x (16-(S-1)) pixels, but the tile's halo is
- * staged ONCE per channel chunk and every tap reads it as a row-shifted window (csrc/conv_tc_halo.cu).  Returns -2
- * outside that envelope. */
+/* Halo-window PERSISTENT tensor-core convolution (csrc/conv_halo.cu), the default for the many-tile stride-1 layers.
+ * Same contract and epilogue as mk_conv2d_tc (ups = 0).  One TMA box per 32-channel chunk lands the (8*RB + R) x 16
+ * pixel halo of a super-tile; every filter tap of every 8 x (17-S) row-block is a row-shifted window of that buffer
+ * (UMMA descriptor start address, 128B swizzle on absolute address bits), the weights stay resident in shared memory
+ * for the life of the CTA when they fit, TMEM accumulators are double-buffered and the output leaves through TMA
+ * stores.  Returns -2 (nothing touched) outside its envelope (R, S <= 4) or when the layer has too few tiles for a
+ * persistent launch - callers then use mk_conv2d_tc.  The _x3 variant is the 3xTF32 mode (wpack mode | 8). */
 int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc, int R, int S,
                       int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
                       float slope, float* y, int Cout_p, int ldy, void* stream);
+int mk_conv2d_tc_halo_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc, int R,
+                         int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
+                         float slope, float* y, int Cout_p, int ldy, void* stream);
+/* dry run of its planner: out[16] = grid.x, cout tiles, RB, smem bytes, halo stages, weight slots, resident?, TMEM
+ * columns, tiles, halo rows, halo stage bytes, weight slot bytes, valid tile width, output groups, acc columns, x3 */
+int mk_conv2d_tc_halo_plan(int N, int Hin, int Win, int Cin_p, int R, int S, int pad, int Cout_p, int has_resid, int x3,
+                           int* out);
 /* dwpack[R*S][Cin_p][Cout_p] = sum over pixels of im2col(x)^T dy  (zero-filled inside). */
 int mk_conv2d_wgrad(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
                     const float* dy, int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream);

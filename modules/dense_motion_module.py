@@ -5,6 +5,8 @@ correction + identity grid] (reference dense_motion_module.py:42-76).  The head 
 (x,y) deformation; the all-zero z column of the reference's (B,d,h,w,3) output exists only at this module's public
 `forward` edge (inside the generator the 2-channel field feeds the grid_sample kernel directly).
 """
+import contextlib
+
 import torch
 from torch import nn
 
@@ -51,9 +53,14 @@ class DenseMotionModule(nn.Module):
         h, w = source_image.shape[3] // step, source_image.shape[4] // step
         src = ops.to_nhwc(source_image, step) if self.mask_embedding.use_deformed_source_image else None
         x = self.mask_embedding.run(src, h, w, kp_driving, kp_source)
-        for block in self.group_blocks:
-            x = block.run(x)  # F.leaky_relu(relu(.), 0.2) of reference line 49 is the identity on a ReLU output
-        pred = self.hourglass.run(x)
+        # The deformation field is GEOMETRY, like the keypoints: a 1e-4 error of a sampling coordinate is multiplied by
+        # the image gradient (unbounded at the zero-padding border of grid_sample), measured 2e-3 ... 2e-2 on
+        # `video_deformed` with 1xTF32 convolutions.  Under the 'auto' policy this network therefore always runs
+        # fp32-accurately (3xTF32); the appearance encoder / decoder keep 1xTF32 for no_grad inference.
+        with (ops.reference_precision() if ops.KP_PRECISE else contextlib.nullcontext()):
+            for block in self.group_blocks:
+                x = block.run(x)  # F.leaky_relu(relu(.), 0.2) of reference line 49 is the identity on a ReLU output
+            pred = self.hourglass.run(x)
         return ops.flow_head(pred, kp_driving, kp_source, self.use_mask, self.use_correction)
 
     def forward(self, source_image, kp_driving, kp_source):

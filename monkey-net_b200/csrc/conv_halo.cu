@@ -1,0 +1,513 @@
+// Halo-window tensor-core convolution for sm_100a: persistent CTAs, resident weights, TMA-store epilogue.
+//
+// k_conv_tc (conv_tc.cu) fetches a shifted 128-pixel A tile once PER FILTER TAP and the weights of that tap once per
+// tile: ncu on 48->48 3x3 @256x256 showed 1.66 GB crossing L2->SM for a 100 MB input (lts throughput 59 %, tensor pipe
+// 14 %) - the many-tile, small-channel layers that dominate the 256x256 configurations are L2->SMEM bound there (the
+// L2 hands every SM ~42 B/clk; an M128 x N48 x K8 TF32 MMA retires in 24 clk).  This kernel removes both re-fetches:
+//
+//   * HALO WINDOWS.  A super-tile is RB row-blocks of 8 rows x TWv columns, TWv = 16 - (S-1).  ONE 4-D TMA box
+//     {32 ch, 16 w, 8*RB + R h, 1 n} per 32-channel chunk lands its halo as 128-byte pixel rows, 16 pixels per image
+//     row, 128B-swizzled (out-of-bounds = zero fill = conv padding).  GEMM row m = 16*row + col of row-block rb and tap
+//     (r, s) is shared-memory row m + 16*(8*rb + r) + s of that buffer, i.e. every tap of every row-block is the SAME
+//     buffer read through a UMMA descriptor whose start address is advanced by whole 128-byte rows.  The 128B swizzle
+//     XORs the 16-byte-chunk bits with ABSOLUTE address bits 7-9 (validated on a B200, tools/halo_probe.py: all 9 / 16
+//     shifted windows agree with the exact kernel at TF32 rounding with descriptor base offset 0), so a row-shifted
+//     window of a 1024-byte-aligned buffer is a legal canonical K-major operand.  Columns >= TWv of each 16-pixel row
+//     are junk GEMM rows the epilogue never stores (87.5 % of the MMA rows useful for 3x3).
+//   * RESIDENT WEIGHTS.  CTAs are persistent (grid = #SMs x cout tiles, static tile striding).  When the packed weights
+//     of the CTA's cout tile fit ([tap][chunk][b_rows x 128 B] <= ~150 KB) they are loaded ONCE per CTA; otherwise they
+//     stream through a ring and the planner picks RB = 2 or 4 so one weight fetch feeds 2-4 accumulators.
+//   * 3xTF32 (mk_conv2d_tc_halo_x3).  Weights carry their lo half behind the hi half (mk_pack_weight mode | 8); the
+//     halo is split hi / lo in shared memory by two dedicated warps (same swizzled layout), and every K step issues
+//     A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same TMEM accumulator.
+//   * DOUBLE-BUFFERED TMEM.  2 x RB accumulators: the epilogue of tile t overlaps the MMAs of tile t+1.
+//   * TMA-STORE EPILOGUE.  tcgen05.ld (thread = pixel) -> bias / affine / residual / activation -> 128B-swizzled
+//     staging rows in shared memory -> cp.async.bulk.tensor store of {32 ch, TWv, 8} boxes: full-line writes, image /
+//     channel edges clipped by the TMA unit.  The residual tile is prefetched by its own TMA producer warp.
+//
+// Warp roles (320 threads): 0 = TMA producer (halo + weights), 1 = MMA issuer, 2 = TMEM allocator + residual producer,
+// 4-7 = epilogue, 8-9 = 3xTF32 splitters.  Envelope: stride 1, no upsample, R, S <= 4, enough tiles to fill the
+// machine (the few-tile deep layers keep k_conv_tc's split-K).  Same contract and epilogue as mk_conv2d_tc.
+#include "common.cuh"
+#include "../../include/monkey_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+using namespace mk_tc;
+
+constexpr int HK = 32;                 // fp32 channels per chunk = 128 bytes
+constexpr int MAXA = 4, MAXB = 40;     // ring depth bounds (MAXB also bounds the resident slots: 9 taps x 4 chunks = 36)
+constexpr int H_SMEM_MAX = 227 * 1024;
+constexpr int H_THREADS = 320;
+
+struct HP {
+    int N, Ho, Wo, Cout_p, Cin_p, R, S, pad;
+    int TWv, RB, tilesW, tilesH, ntiles;
+    int halo_rows, a_half, a_stage, a_stages;
+    int b_rows, b_half, b_slot, b_slots, resident;
+    int nchunks, ngroups, npad, tmem_cols;
+    int x3, lo_tap_offset;
+    int stg_bytes, nstg;   // nstg = 1 or 2 staging buffers (and as many residual buffers)
+    const float* scale; const float* shift; int has_resid, act; float slope;
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(H_THREADS, 1)
+k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const HP p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = a_ring + p.a_stages * p.a_stage;
+    uint8_t* stg = b_ring + p.b_slots * p.b_slot;             // nstg output staging buffers
+    uint8_t* rbuf = stg + p.nstg * p.stg_bytes;               // nstg residual buffers (has_resid only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rbuf + (p.has_resid ? p.nstg * p.stg_bytes : 0));
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + MAXA;
+    uint64_t* a_split = a_empty + MAXA;
+    uint64_t* b_full = a_split + MAXA;
+    uint64_t* b_empty = b_full + MAXB;
+    uint64_t* tmem_full = b_empty + MAXB;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* r_full = tmem_empty + 2;
+    uint64_t* r_empty = r_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cout0 = blockIdx.y * 128;
+    const int n_this = min(128, p.Cout_p - cout0);
+    const int ngroups = (n_this + 31) >> 5;
+    const int ntaps = p.R * p.S;
+    const int tiles_per_img = p.tilesW * p.tilesH;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+        if (p.has_resid) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < MAXA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_split[i], 2); }
+        for (int i = 0; i < MAXB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
+            mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer: halo + weights
+        if (elect_one()) {
+            int ai = 0, bi = 0;
+            for (int tile = blockIdx.x, lt = 0; tile < p.ntiles; tile += gridDim.x, ++lt) {
+                const int n = tile / tiles_per_img, trem = tile - n * tiles_per_img;
+                const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
+                const int w0 = tw * p.TWv, h0 = th * 8 * p.RB;
+                for (int ch = 0; ch < p.nchunks; ++ch, ++ai) {
+                    const int as = ai % p.a_stages;
+                    mbar_wait(&a_empty[as], ((ai / p.a_stages) & 1) ^ 1);
+                    mbar_expect_tx(&a_full[as], p.a_half);
+                    tma_load_4d(a_ring + as * p.a_stage, &tmA, &a_full[as], ch * HK, w0 - p.pad, h0 - p.pad, n);
+                    if (p.resident && lt > 0) continue;
+                    for (int tap = 0; tap < ntaps; ++tap) {
+                        int bs;
+                        if (p.resident) {
+                            bs = ch * ntaps + tap;
+                        } else {
+                            bs = bi % p.b_slots;
+                            mbar_wait(&b_empty[bs], ((bi / p.b_slots) & 1) ^ 1);
+                            ++bi;
+                        }
+                        uint8_t* b = b_ring + bs * p.b_slot;
+                        mbar_expect_tx(&b_full[bs], p.b_half << p.x3);
+                        tma_load_3d(b, &tmB, &b_full[bs], ch * HK, cout0, tap);
+                        if (p.x3) tma_load_3d(b + p.b_half, &tmB, &b_full[bs], ch * HK, cout0, p.lo_tap_offset + tap);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        const uint32_t idesc = umma_idesc_tf32(128, (n_this + 15) & ~15);
+        int ai = 0, bi = 0;
+        for (int tile = blockIdx.x, lt = 0; tile < p.ntiles; tile += gridDim.x, ++lt) {
+            const int buf = lt & 1;
+            mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int ch = 0; ch < p.nchunks; ++ch, ++ai) {
+                const int as = ai % p.a_stages;
+                mbar_wait(p.x3 ? &a_split[as] : &a_full[as], (ai / p.a_stages) & 1);
+                int kleft = p.Cin_p - ch * HK;
+                if (kleft > HK) kleft = HK;
+                const int nk = (kleft + 7) >> 3;
+                const uint8_t* a = a_ring + as * p.a_stage;
+                for (int tap = 0; tap < ntaps; ++tap) {
+                    int bs;
+                    if (p.resident) {
+                        bs = ch * ntaps + tap;
+                        if (lt == 0) mbar_wait(&b_full[bs], 0);
+                    } else {
+                        bs = bi % p.b_slots;
+                        mbar_wait(&b_full[bs], (bi / p.b_slots) & 1);
+                        ++bi;
+                    }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const int r = tap / p.S, s = tap - r * p.S;
+                        const uint8_t* b = b_ring + bs * p.b_slot;
+                        const uint64_t bdesc = umma_desc(b);
+                        const uint64_t bldesc = umma_desc(b + p.b_half);
+                        for (int rb = 0; rb < p.RB; ++rb) {
+                            const uint8_t* aw = a + ((8 * rb + r) * 16 + s) * 128;   // row-shifted window, base offset 0
+                            const uint64_t adesc = umma_desc(aw);
+                            const uint32_t d = tmem_base + (uint32_t)((buf * p.RB + rb) * p.npad);
+                            if (p.x3) {
+                                const uint64_t aldesc = umma_desc(aw + p.a_half);
+                                for (int k = 0; k < nk; ++k) {
+                                    umma_tf32(d, aldesc + 2 * k, bdesc + 2 * k, idesc, (ch | tap | k) ? 1u : 0u);
+                                    umma_tf32(d, adesc + 2 * k, bldesc + 2 * k, idesc, 1u);
+                                    umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                                }
+                            } else {
+                                for (int k = 0; k < nk; ++k)
+                                    umma_tf32(d, adesc + 2 * k, bdesc + 2 * k, idesc, (ch | tap | k) ? 1u : 0u);
+                            }
+                        }
+                        if (!p.resident) umma_commit(&b_empty[bs]);
+                        if (tap == ntaps - 1) {
+                            umma_commit(&a_empty[as]);
+                            if (ch == p.nchunks - 1) umma_commit(&tmem_full[buf]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================================================== residual producer
+        if (p.has_resid && elect_one()) {
+            int gi = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                const int n = tile / tiles_per_img, trem = tile - n * tiles_per_img;
+                const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
+                const int w0 = tw * p.TWv, h0 = th * 8 * p.RB;
+                for (int rb = 0; rb < p.RB; ++rb)
+                    for (int g = 0; g < ngroups; ++g, ++gi) {
+                        const int sb = p.nstg == 2 ? (gi & 1) : 0;
+                        mbar_wait(&r_empty[sb], ((p.nstg == 2 ? gi >> 1 : gi) & 1) ^ 1);
+                        mbar_expect_tx(&r_full[sb], p.stg_bytes);
+                        tma_load_4d(rbuf + sb * p.stg_bytes, &tmR, &r_full[sb], cout0 + g * 32, w0, h0 + 8 * rb, n);
+                    }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================================================================== 3xTF32 halo splitters (64 threads)
+        if (p.x3) {
+            const int tid = threadIdx.x - 256;
+            const int n4 = p.a_half >> 4;
+            int ai = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+                for (int ch = 0; ch < p.nchunks; ++ch, ++ai) {
+                    const int as = ai % p.a_stages;
+                    mbar_wait(&a_full[as], (ai / p.a_stages) & 1);
+                    float4* hi = reinterpret_cast<float4*>(a_ring + as * p.a_stage);
+                    float4* lo = reinterpret_cast<float4*>(a_ring + as * p.a_stage + p.a_half);
+#pragma unroll 4
+                    for (int i = tid; i < n4; i += 64) {
+                        float4 v = hi[i], h, l;
+                        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                        split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                        hi[i] = h;
+                        lo[i] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_split[as]);
+                }
+        }
+    } else if (warp >= 4) {
+        // ===================================================================== epilogue (warps 4-7)
+        const int q = warp & 3;
+        const int m = q * 32 + lane;              // TMEM lane = GEMM row = 16 * tile row + tile column
+        const int col = m & 15, row = m >> 4;
+        const bool valid = col < p.TWv;
+        const int srow = row * p.TWv + col;       // row of the dense {32 ch, TWv, 8} staging box
+        const int sw = srow & 7;                  // 128B swizzle phase of that row (buffers are 1024-byte aligned)
+        const bool leader = threadIdx.x == 128;
+        int gi = 0;
+        for (int tile = blockIdx.x, lt = 0; tile < p.ntiles; tile += gridDim.x, ++lt) {
+            const int n = tile / tiles_per_img, trem = tile - n * tiles_per_img;
+            const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
+            const int w0 = tw * p.TWv, h0 = th * 8 * p.RB;
+            const int buf = lt & 1;
+            mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int rb = 0; rb < p.RB; ++rb) {
+                const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.RB + rb) * p.npad);
+                for (int g = 0; g < ngroups; ++g, ++gi) {
+                    const int sb = p.nstg == 2 ? (gi & 1) : 0;
+                    uint8_t* sbuf = stg + sb * p.stg_bytes;
+                    // staging buffer sb was handed to the TMA store nstg groups ago: its smem read must be complete
+                    if (leader) {
+                        if (p.nstg == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    if (p.has_resid) mbar_wait(&r_full[sb], (p.nstg == 2 ? gi >> 1 : gi) & 1);
+                    epi_bar();
+                    const int cbase = g * 32;
+                    const int cn = min(32, n_this - cbase);           // multiple of 4
+                    float v[32];
+                    tmem_ld16(tacc + (uint32_t)cbase, v);
+                    if (cn > 16) tmem_ld16(tacc + (uint32_t)(cbase + 16), v + 16);
+                    if (valid) {
+                        const float4* rrow = reinterpret_cast<const float4*>(rbuf + sb * p.stg_bytes + srow * 128);
+                        float4* orow = reinterpret_cast<float4*>(sbuf + srow * 128);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (4 * j >= cn) break;
+                            const int co = cout0 + cbase + 4 * j;
+                            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (p.scale) o = o * ldg4(p.scale + co);
+                            if (p.shift) o = o + ldg4(p.shift + co);
+                            if (p.has_resid) o = o + rrow[j ^ sw];
+                            if (p.act == 1) {
+                                o.x = o.x > 0.f ? o.x : o.x * p.slope; o.y = o.y > 0.f ? o.y : o.y * p.slope;
+                                o.z = o.z > 0.f ? o.z : o.z * p.slope; o.w = o.w > 0.f ? o.w : o.w * p.slope;
+                            } else if (p.act == 2) {
+                                o.x = 1.f / (1.f + expf(-o.x)); o.y = 1.f / (1.f + expf(-o.y));
+                                o.z = 1.f / (1.f + expf(-o.z)); o.w = 1.f / (1.f + expf(-o.w));
+                            }
+                            orow[j ^ sw] = o;
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> TMA store reads
+                    __syncwarp();
+                    if (p.has_resid && lane == 0) mbar_arrive(&r_empty[sb]);       // residual buffer consumed
+                    epi_bar();
+                    if (leader) {
+                        tma_store_4d(&tmY, sbuf, cout0 + cbase, w0, h0 + 8 * rb, n);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            }
+            // every accumulator of this tile has been read: hand the TMEM buffer back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                     : "memory");
+    }
+}
+
+}  // namespace
+
+static thread_local int t_hx3 = 0;
+static thread_local int* t_hplan = nullptr;
+
+// Returns 0 on success, -2 when the shape is outside this kernel's envelope or the launch would leave most SMs idle
+// (callers use mk_conv2d_tc, whose split-K serves the few-tile layers).
+MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc,
+                                int R, int S, int pad, const float* scale, const float* shift, const float* resid,
+                                int ldr, int act, float slope, float* y, int Cout_p, int ldy, void* stream) {
+    const int Ho = Hin + 2 * pad - R + 1, Wo = Win + 2 * pad - S + 1;
+    if (Cin_p % 4 || ldx % 4 || Cout_p % 4 || ldy % 4 || (resid && ldr % 4) || R < 1 || S < 1 || R > 4 || S > 4 ||
+        Ho < 1 || Wo < 1) {
+        mk_set_error("mk_conv2d_tc_halo: outside the halo kernel's envelope");
+        return -2;
+    }
+    HP p;
+    p.x3 = t_hx3;
+    p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout_p = Cout_p; p.Cin_p = Cin_p; p.R = R; p.S = S; p.pad = pad;
+    p.TWv = 16 - (S - 1);
+    p.tilesW = (Wo + p.TWv - 1) / p.TWv;
+    p.nchunks = (Cin_p + HK - 1) / HK;
+    p.lo_tap_offset = R * S;
+    const int n_tile = Cout_p < 128 ? Cout_p : 128;
+    p.b_rows = (n_tile + 15) & ~15;
+    p.b_half = p.b_rows * 128;
+    p.b_slot = p.b_half << p.x3;
+    p.ngroups = (n_tile + 31) / 32;
+    p.npad = p.b_rows;
+    p.stg_bytes = p.TWv * 8 * 128;
+    p.has_resid = resid ? 1 : 0;
+    p.scale = scale; p.shift = shift; p.act = act; p.slope = slope;
+    const int cout_tiles = (Cout_p + 127) / 128;
+    const int sms = mk_num_sms();
+    const int nB = R * S * p.nchunks;
+    // K steps of one tap summed over the chunks, and the weight bytes one pass over all (tap, chunk) pairs fetches
+    int ksteps = 0;
+    for (int ch = 0; ch < p.nchunks; ++ch) ksteps += ((Cin_p - ch * HK > HK ? HK : Cin_p - ch * HK) + 7) >> 3;
+    const double w_bytes = (double)R * S * Cin_p * p.b_rows * 4 * (p.x3 ? 2 : 1);
+    // Planner: for RB in {1, 2, 4} and {2, 1} staging buffers find whether the weights can stay resident, and model the
+    // time per 8-row block as max(MMA floor, L2->SM bytes / 40 B per clk) x the wave-quantisation loss of the static
+    // tile striding.  Smallest modelled time wins; ties go to the smaller RB.
+    double best_score = 0.0;
+    int best_rb = 0, best_nstg = 0, best_res = 0;
+    for (int rb = 1; rb <= 4; rb <<= 1) {
+        if (2 * rb * p.npad > 512) break;                                  // double-buffered accumulators in TMEM
+        if (rb > 1 && 8 * (rb / 2) >= Ho) break;                           // the extra row-blocks would all be empty
+        const int halo_rows = 8 * rb + R;                                   // (R-1) halo rows + 1 overrun row
+        const int a_stage = (halo_rows * 16 * 128) << p.x3;
+        int nstg = 0, res = 0;
+        for (int ns = 2; ns >= 1 && !nstg; --ns) {
+            const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + 2048;
+            if (nB <= MAXB && nB * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) { nstg = ns; res = 1; }
+            else if (2 * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX && ns == 1) { nstg = ns; res = 0; }
+            else if (3 * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) { nstg = ns; res = 0; }
+        }
+        if (!nstg) break;
+        const double mma_clk = (double)rb * R * S * ksteps * (128.0 * p.b_rows / 256.0) * (p.x3 ? 3 : 1);
+        const double a_bytes = (double)halo_rows * 16 * Cin_p * 4;
+        const double l2 = a_bytes + (res ? 0.0 : w_bytes) + (double)rb * (1 + p.has_resid) * p.TWv * 8 * n_tile * 4;
+        const long long tiles = (long long)p.tilesW * ((Ho + 8 * rb - 1) / (8 * rb)) * N;
+        int gx = sms / cout_tiles < 1 ? 1 : sms / cout_tiles;
+        const double waves = (double)tiles / gx;
+        const double quant = (double)((tiles + gx - 1) / gx) / (waves > 1e-9 ? waves : 1e-9);
+        const double rows_eff = (double)Ho / ((Ho + 8 * rb - 1) / (8 * rb) * 8.0 * rb);
+        const double score = (mma_clk > l2 / 40.0 ? mma_clk : l2 / 40.0) / rb * quant / rows_eff;
+        if (!best_rb || score < best_score * 0.97) { best_rb = rb; best_score = score; best_nstg = nstg; best_res = res; }
+    }
+    if (!best_rb) {
+        mk_set_error("mk_conv2d_tc_halo: no shared-memory plan for this layer");
+        return -2;
+    }
+    p.RB = best_rb;
+    p.nstg = best_nstg;
+    p.resident = best_res;
+    p.halo_rows = 8 * p.RB + R;
+    p.a_half = p.halo_rows * 16 * 128;
+    p.a_stage = p.a_half << p.x3;
+    p.tilesH = (Ho + 8 * p.RB - 1) / (8 * p.RB);
+    p.ntiles = p.tilesW * p.tilesH * N;
+    // envelope of the persistent launch: enough tiles for two waves, and tiles that are mostly inside the image
+    // (small / deep levels: 16-wide rows of a 16x16 image would be 57 % junk; mk_conv2d_tc's split-K serves them)
+    const double useful = (double)Ho * Wo / ((double)p.tilesH * 8 * p.RB * p.tilesW * p.TWv);
+    if ((long long)p.ntiles * cout_tiles < 2LL * sms || useful < 0.7) {
+        mk_set_error("mk_conv2d_tc_halo: %d tiles, %.0f %% useful: left to mk_conv2d_tc", p.ntiles, 100.0 * useful);
+        return -2;
+    }
+    const int fixed = p.nstg * (1 + p.has_resid) * p.stg_bytes + 2048 /*barriers + alignment*/;
+    int budget = H_SMEM_MAX - fixed;
+    if (p.resident) {
+        p.b_slots = nB;
+        p.a_stages = (budget - nB * p.b_slot) / p.a_stage;
+    } else {
+        // streaming: two halo stages, the rest of the budget holds weight slots (at most 8: more buy nothing, and a
+        // third halo stage is worth more)
+        p.a_stages = 2;
+        p.b_slots = (budget - 2 * p.a_stage) / p.b_slot;
+        if (p.b_slots > 8) {
+            p.b_slots = 8;
+            if (budget - 8 * p.b_slot >= 3 * p.a_stage) p.a_stages = 3;
+        }
+    }
+    if (p.a_stages > MAXA) p.a_stages = MAXA;
+    MK_REQUIRE(p.a_stages >= 2 && (p.resident || p.b_slots >= 2), "mk_conv2d_tc_halo: ring plan failed");
+    const int cols = 2 * p.RB * p.npad;
+    p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
+    const int smem_bytes = p.a_stages * p.a_stage + p.b_slots * p.b_slot + fixed;
+    MK_REQUIRE(smem_bytes <= H_SMEM_MAX, "mk_conv2d_tc_halo: shared memory plan exceeds 227 KB (%d)", smem_bytes);
+    int grid_x = sms / cout_tiles;
+    if (grid_x < 1) grid_x = 1;
+    if (grid_x > p.ntiles) grid_x = p.ntiles;
+    if (t_hplan) {
+        int* o = t_hplan;
+        o[0] = grid_x; o[1] = cout_tiles; o[2] = p.RB; o[3] = smem_bytes; o[4] = p.a_stages; o[5] = p.b_slots;
+        o[6] = p.resident; o[7] = p.tmem_cols; o[8] = p.ntiles; o[9] = p.halo_rows; o[10] = p.a_stage; o[11] = p.b_slot;
+        o[12] = p.TWv; o[13] = p.ngroups; o[14] = p.npad; o[15] = p.x3 | (p.nstg << 1);
+        return 0;
+    }
+    EncodeTiledFn encode = get_encode();
+    MK_REQUIRE(encode != nullptr, "mk_conv2d_tc_halo: cuTensorMapEncodeTiled unavailable");
+    CUtensorMap tmA, tmB, tmY, tmR;
+    cuuint32_t es4[4] = {1, 1, 1, 1};
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin_p, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)Win * ldx * 4, (cuuint64_t)Hin * Win * ldx * 4};
+        cuuint32_t box[4] = {(cuuint32_t)HK, 16, (cuuint32_t)p.halo_rows, 1};
+        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, es4,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: activation tensor map rejected (%d)", (int)r);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S * (p.x3 ? 2 : 1))};
+        cuuint64_t strides[2] = {(cuuint64_t)Cin_p * 4, (cuuint64_t)Cin_p * Cout_p * 4};
+        cuuint32_t box[3] = {(cuuint32_t)HK, (cuuint32_t)p.b_rows, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wpack_tc), dims, strides, box,
+                            es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: weight tensor map rejected (%d)", (int)r);
+    }
+    for (int which = 0; which < 2; ++which) {
+        if (which == 1 && !resid) { tmR = tmY; break; }
+        const float* base = which ? resid : y;
+        const int ld = which ? ldr : ldy;
+        cuuint64_t dims[4] = {(cuuint64_t)Cout_p, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)Wo * ld * 4, (cuuint64_t)Ho * Wo * ld * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.TWv, 8, 1};
+        CUresult r = encode(which ? &tmR : &tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims,
+                            strides, box, es4, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: output tensor map rejected (%d)", (int)r);
+    }
+    static unsigned long long attr_done = 0;
+    if (const unsigned long long attr_bit = mk_attr_needed(attr_done)) {
+        cudaError_t e = cudaFuncSetAttribute(k_conv_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, H_SMEM_MAX);
+        if (e != cudaSuccess) { mk_set_error("mk_conv2d_tc_halo: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_done |= attr_bit;
+    }
+    dim3 grid((unsigned)grid_x, (unsigned)cout_tiles, 1);
+    k_conv_halo<<<grid, H_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmY, tmR, p);
+    return mk_check_launch("mk_conv2d_tc_halo");
+}
+
+MK_EXPORT int mk_conv2d_tc_halo_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc,
+                                   int R, int S, int pad, const float* scale, const float* shift, const float* resid,
+                                   int ldr, int act, float slope, float* y, int Cout_p, int ldy, void* stream) {
+    t_hx3 = 1;
+    const int rc = mk_conv2d_tc_halo(x, N, Hin, Win, Cin_p, ldx, wpack_tc, R, S, pad, scale, shift, resid, ldr, act, slope,
+                                     y, Cout_p, ldy, stream);
+    t_hx3 = 0;
+    return rc;
+}
+
+// Dry run of the planner (no device state touched): out[16] = grid.x, grid.y (cout tiles), RB, dynamic smem bytes,
+// halo stages, weight slots, weights resident?, TMEM columns, tiles, halo rows, halo stage bytes, weight slot bytes,
+// valid tile width, 32-channel output groups, accumulator columns, x3.  Returns -2 outside the envelope.
+MK_EXPORT int mk_conv2d_tc_halo_plan(int N, int Hin, int Win, int Cin_p, int R, int S, int pad, int Cout_p, int has_resid,
+                                     int x3, int* out) {
+    MK_REQUIRE(out != nullptr, "mk_conv2d_tc_halo_plan: out is NULL");
+    t_hplan = out;
+    t_hx3 = x3 ? 1 : 0;
+    static float dummy;
+    const int rc = mk_conv2d_tc_halo(nullptr, N, Hin, Win, Cin_p, Cin_p, nullptr, R, S, pad, nullptr, nullptr,
+                                     has_resid ? &dummy : nullptr, Cout_p, 0, 0.f, nullptr, Cout_p, Cout_p, nullptr);
+    t_hplan = nullptr;
+    t_hx3 = 0;
+    return rc;
+}

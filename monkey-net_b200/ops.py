@@ -67,9 +67,10 @@ _PRECISE = [0]
 
 class reference_precision:
     """Context: under the 'auto' policy run the enclosed convolutions fp32-accurately (3xTF32) even without autograd.
-    The keypoint detector uses it (KP_PRECISE): the north-star asks for bit-exact keypoint pixel indices, and a 1xTF32
-    hourglass moves the soft-argmax by ~5e-5 - enough to flip a rounded pixel coordinate that sits next to a .5
-    boundary.  The generator's 1e-3 frame bar is met by 1xTF32."""
+    The two GEOMETRY networks use it (KP_PRECISE): the keypoint detector - the north-star asks for bit-exact keypoint
+    pixel indices, and a 1xTF32 hourglass moves the soft-argmax by ~5e-5, enough to flip a rounded pixel coordinate
+    next to a .5 boundary - and the dense-motion network, whose sampling coordinates are amplified by image gradients
+    (`video_deformed` off by 2e-3..2e-2 with 1xTF32).  The appearance path meets the 1e-3 frame bar with 1xTF32."""
 
     def __enter__(self):
         _PRECISE[0] += 1
@@ -89,32 +90,27 @@ def conv_mode():
     return CONV_MODE
 
 
-# EXPERIMENTAL halo-window tensor-core conv (csrc/conv_tc_halo.cu): opt-in, not validated on hardware yet
-CONV_HALO = os.environ.get('MONKEY_B200_CONV_HALO', '0') == '1'
+# Halo-window persistent tensor-core conv (csrc/conv_halo.cu): the default for the many-tile stride-1 layers; the entry
+# point declines (-2, before touching device state) shapes outside its envelope and few-tile layers, which run on
+# mk_conv2d_tc (split-K).  MONKEY_B200_CONV_HALO=0 switches it off.
+CONV_HALO = os.environ.get('MONKEY_B200_CONV_HALO', '1') != '0'
 
 
-def _halo_ok(N, Hin, Win, R, S, pad, ups, groups, cop):
-    if not CONV_HALO or ups or R != S or R not in (3, 4):
-        return False
-    Ho, Wo = Hin + 2 * pad - R + 1, Win + 2 * pad - S + 1
-    twv = 16 - (S - 1)
-    if Ho < 8 or Wo < twv:
-        return False
-    tiles = N * ((Ho + 7) // 8) * ((Wo + twv - 1) // twv) * ((cop + 127) // 128)
-    return tiles >= 148  # the many-tile, L2-bound layers; the few-tile ones keep split-K
+def _tc_launch(xp, N, Hin, Win, Cp, ups, wp, R, S, pad, scale, shift, resid_ptr, ldr, act, slope, yp, Cop, st, x3=False):
+    """one tensor-core convolution launch on raw pointers: halo kernel when it takes the shape, else the per-tap one"""
+    if CONV_HALO and not ups:
+        rc = lib.call_soft('mk_conv2d_tc_halo_x3' if x3 else 'mk_conv2d_tc_halo', (-2,), xp, N, Hin, Win, Cp, Cp, wp,
+                           R, S, pad, scale, shift, resid_ptr, ldr, act, slope, yp, Cop, Cop, st)
+        if rc == 0:
+            return
+    lib.call('mk_conv2d_tc_x3' if x3 else 'mk_conv2d_tc', xp, N, Hin, Win, Cp, Cp, ups, wp, R, S, pad, scale, shift,
+             resid_ptr, ldr, act, slope, yp, Cop, Cop, st)
 
 
 def _conv_tc_call(x, N, Hin, Win, Cp, ups, wpack, R, S, pad, scale, shift, resid_ptr, ldr, act, slope, y, Cop, groups, st,
                   x3=False):
-    if x3:
-        lib.call('mk_conv2d_tc_x3', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, scale, shift,
-                 resid_ptr, ldr, act, slope, y.data_ptr(), Cop, Cop, st)
-    elif _halo_ok(N, Hin, Win, R, S, pad, ups, groups, Cop):
-        lib.call('mk_conv2d_tc_halo', x.data_ptr(), N, Hin, Win, Cp, Cp, wpack.data_ptr(), R, S, pad, scale, shift,
-                 resid_ptr, ldr, act, slope, y.data_ptr(), Cop, Cop, st)
-    else:
-        lib.call('mk_conv2d_tc', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, wpack.data_ptr(), R, S, pad, scale, shift,
-                 resid_ptr, ldr, act, slope, y.data_ptr(), Cop, Cop, st)
+    _tc_launch(x.data_ptr(), N, Hin, Win, Cp, ups, wpack.data_ptr(), R, S, pad, scale, shift, resid_ptr, ldr, act, slope,
+               y.data_ptr(), Cop, st, x3)
 
 
 def set_conv_mode(mode):
@@ -315,7 +311,6 @@ class _Conv(torch.autograd.Function):
         dx = dw = db = None
         tc = ctx.mode != 'fp32'
         x3 = ctx.mode == 'tf32x3'
-        conv_tc = 'mk_conv2d_tc_x3' if x3 else 'mk_conv2d_tc'
         if ctx.needs_input_grad[0]:
             wt = _empty(R * S * Cop * Cp * (2 if x3 else 1), like=x)
             lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop,
@@ -326,13 +321,13 @@ class _Conv(torch.autograd.Function):
             # the full-resolution gradient is pooled by the (x4, average) mode of the norm-apply kernel.
             if tc and ups:
                 full = _empty(N, dy.shape[1], dy.shape[2], Cp, like=x)
-                lib.call(conv_tc, dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
-                         R - 1 - pad, None, None, None, 0, 0, 0.0, full.data_ptr(), Cp, Cp, st)
+                _tc_launch(dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, 0, wt.data_ptr(), R, S, R - 1 - pad, None,
+                           None, None, 0, 0, 0.0, full.data_ptr(), Cp, st, x3)
                 lib.call('mk_norm_apply', full.data_ptr(), Cp, N, dy.shape[1], dy.shape[2], Cp,
                          _times4_params(Cp, x.device).data_ptr(), 0, -1.0, 1, dx.data_ptr(), Cp, st)
             elif tc:
-                lib.call(conv_tc, dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
-                         R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, st)
+                _tc_launch(dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, 0, wt.data_ptr(), R, S, R - 1 - pad, None,
+                           None, None, 0, 0, 0.0, dx.data_ptr(), Cp, st, x3)
             else:
                 lib.call('mk_conv2d', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
                          R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, 2 if ups else 0, st)

@@ -158,20 +158,18 @@ def test_wgrad_kernels_match_torch_autograd(cin, cout, k, pad, H, W, N, kernel):
     assert err < KERNEL_TOL[kernel] * (2 if kernel == 'tf32x3' else 1), err
 
 
-def test_train_step_tf32_mode_gradients():
-    """G-step gradients with every conv (fwd, dgrad, wgrad) on tensor cores vs the fp32 oracle: TF32-level agreement."""
+def _grad_cosines(cfg, res, batch, mode):
     from monkey_net_b200 import ops, train_step
     from oracle import monkey_oracle as mo
     import test_gpu_2_modules as t2
-    cfg = helpers.load_config('shapes')
-    (gen, disc, kp), (og, od, ok), x = t2._pair(cfg, 64, 2)
+    (gen, disc, kp), (og, od, ok), x = t2._pair(cfg, res, batch)
     tp = cfg['train_params']
     for m in (gen, disc, kp, og, od, ok):
         m.train()
     out = mo.generator_full(ok, og, od, tp, x)
     sum(v.mean() for v in out[:-2]).backward()
     prev = ops.CONV_MODE
-    ops.set_conv_mode('tf32')
+    ops.set_conv_mode(mode)
     try:
         pout = train_step.GeneratorFullModel(kp, gen, disc, tp)({k: v.cuda() for k, v in x.items()})
         sum(v.mean() for v in pout[:-2]).backward()
@@ -185,13 +183,32 @@ def test_train_step_tf32_mode_gradients():
         a, b = p1.grad.detach().cpu().flatten(), p2.grad.flatten()
         coss.append((float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)), n1))
     coss.sort()
+    return coss
+
+
+def test_train_step_tf32_mode_gradients():
+    """EXPLICIT 'tf32' mode (every conv 1xTF32; not the training default): G-step gradients vs the fp32 oracle."""
+    coss = _grad_cosines(helpers.load_config('shapes'), 64, 2, 'tf32')
     med = coss[len(coss) // 2][0]
     print('tf32 train step: gradient cosine vs fp32 oracle: median %.5f, 5 worst %s' % (med, coss[:5]))
     # TF32 (10-bit mantissa) through ~25 conv+BN layers and the warp's d(grid).  The fp32 reference algorithm itself
     # turns 5e-4 relative conv-output noise into median-cosine 0.97 / worst 0.90 gradients (tools/noise_sensitivity.py),
-    # so that is the envelope a TF32 implementation can be held to (worst-case bar with margin for the run-to-run
-    # spread of the atomics' summation order: median 0.94-0.98, worst 0.82-0.90 observed).
+    # so that is the envelope a 1xTF32 implementation can be held to - the reason training defaults to 3xTF32.
     assert med > 0.9 and coss[0][0] > 0.7, coss[:5]
+
+
+@pytest.mark.parametrize('name,res,batch', [('tiny', 32, 3), ('shapes', 64, 2)])
+def test_train_step_default_mode_gradient_cosine(name, res, batch):
+    """The product's DEFAULT training arithmetic ('auto' -> 3xTF32 tensor-core convolutions): composed G-step
+    parameter gradients against the fp32 CPU oracle, cosine per parameter tensor.  Bar: median >= 0.9999 (SURVEY
+    8(c)); the tail is bounded by the reference's own conditioning (tools/noise_sensitivity_tiny.py: 1e-6 relative
+    noise on the oracle's conv outputs moves single gradients by up to 2e-1)."""
+    cfg = helpers.tiny_config() if name == 'tiny' else helpers.load_config(name)
+    coss = _grad_cosines(cfg, res, batch, 'auto')
+    med, p10 = coss[len(coss) // 2][0], coss[len(coss) // 10][0]
+    print('%s auto (3xTF32) train step: gradient cosine vs fp32 oracle: median %.6f, 10th percentile %.6f, 5 worst %s'
+          % (name, med, p10, coss[:5]))
+    assert med >= 0.9999 and p10 >= 0.999 and coss[0][0] > 0.9, coss[:5]
 
 
 def test_conv_tc_rejects_unsupported_shapes_without_touching_output():
@@ -205,18 +222,22 @@ def test_conv_tc_rejects_unsupported_shapes_without_touching_output():
                  y.data_ptr(), 16, 16, torch.cuda.current_stream().cuda_stream)
 
 
+@pytest.mark.parametrize('mode', ['auto', 'tf32'])
 @pytest.mark.parametrize('name,res', [('taichi', 64), ('shapes', 64)])
-def test_generator_tf32_mode_against_oracle(name, res):
-    """Whole generator + keypoint detector with the tensor-core convs; bar = north-star 1e-3 on the frame."""
+def test_generator_tensor_core_modes_against_oracle(name, res, mode):
+    """Whole keypoint detector + generator, eval / no_grad, against the fp32 CPU oracle.
+      'auto' (product default, what bench.py times): geometry networks 3xTF32, appearance path 1xTF32 -
+             keypoints <= 2e-5 AND identical pixel indices (the logger.py:99-100 rule, north-star "bit-exact"),
+             frame <= 1e-3 (north-star), deformed frame <= 1e-3;
+      'tf32' (everything 1xTF32): frame <= 1e-3, keypoints <= 1e-4 (pixel indices may flip next to a .5 boundary)."""
     from monkey_net_b200 import ops
-    from oracle import monkey_oracle as mo
     import test_gpu_2_modules as t2
     cfg = helpers.load_config(name)
     (gen, disc, kp), (og, od, ok), x = t2._pair(cfg, res, 2, d=1)
     for m in (gen, kp, og, ok):
         m.eval()
     prev = ops.CONV_MODE
-    ops.set_conv_mode('tf32')
+    ops.set_conv_mode(mode)
     try:
         with torch.no_grad():
             a = kp(x['video'].cuda())
@@ -230,31 +251,38 @@ def test_generator_tf32_mode_against_oracle(name, res):
     e_kp = helpers.max_abs(a['mean'], b['mean'])
     e_pred = helpers.max_abs(ga['video_prediction'], oa['video_prediction'])
     e_def = helpers.max_abs(ga['video_deformed'], oa['video_deformed'])
-    print('tf32 mode %s: |kp mean| %.2e  |prediction| %.2e  |deformed| %.2e' % (name, e_kp, e_pred, e_def))
-    assert e_kp < 2e-3 and e_pred < 5e-3
+    same_px = torch.equal(torch.round(res * (a['mean'].cpu() + 1) / 2), torch.round(res * (b['mean'] + 1) / 2))
+    print('%s mode %s: |kp mean| %.2e  |prediction| %.2e  |deformed| %.2e  identical pixel indices: %s'
+          % (mode, name, e_kp, e_pred, e_def, same_px))
+    assert e_pred < 1e-3
+    if mode == 'auto':
+        assert e_kp < 2e-5 and same_px and e_def < 1e-3
+    else:
+        assert e_kp < 1e-4
 
 
-# ------------------------------------------------------------------------------------------------ experimental
-import os  # noqa: E402
-
+# ------------------------------------------------------------------------------------------------ halo-window kernel
 HALO_CASES = [
     # cin, cout, k, pad, H, W, N, resid, act
-    (24, 24, 3, 1, 64, 64, 4, False, 0),
-    (48, 48, 3, 1, 32, 40, 2, True, 1),
-    (4, 32, 3, 1, 32, 32, 2, False, 0),
-    (64, 128, 4, 0, 29, 29, 2, False, 0),
-    (160, 32, 3, 1, 16, 16, 2, False, 0),     # 5 channel chunks: both rings wrap
-    (32, 144, 3, 1, 17, 21, 2, False, 2),     # two cout tiles, partial tiles in both directions
+    (48, 48, 3, 1, 64, 64, 16, True, 1),      # refinement ResBlock conv of taichi: 2 chunks, resident weights, residual
+    (24, 24, 3, 1, 64, 64, 32, True, 0),      # shapes.yaml ResBlock
+    (4, 32, 3, 1, 64, 64, 8, False, 0),       # image input: 4 physical channels ride on the TMA zero fill
+    (64, 128, 4, 0, 61, 61, 8, False, 0),     # discriminator 4x4 valid, TWv = 13, 4 output groups
+    (160, 32, 3, 1, 64, 64, 8, False, 1),     # 5 channel chunks: 45 weight slots -> streaming ring
+    (32, 144, 3, 1, 60, 52, 8, False, 2),     # two cout tiles (128 + 16), partial tiles both ways, sigmoid
+    (44, 44, 1, 0, 64, 64, 12, False, 0),     # 1x1 (TWv = 16)
+    (16, 64, 4, 3, 61, 61, 8, False, 0),      # dgrad of a 4x4 valid conv: full correlation, pad 3
+    (64, 128, 3, 1, 64, 64, 16, False, 0),    # weights do not fit: streaming, several row-blocks per super-tile
+    (48, 48, 3, 1, 61, 50, 10, True, 1),      # H, W not multiples of the tile
+    (128, 32, 3, 1, 64, 64, 8, False, 0),     # 36 resident weight slots
+    (36, 12, 3, 1, 64, 64, 16, False, 0),     # hourglass head: Cout_p = 12 (one 16-column accumulator)
 ]
 
 
-@pytest.mark.skipif(os.environ.get('MONKEY_B200_CONV_HALO', '0') != '1',
-                    reason='experimental halo-window conv (csrc/conv_tc_halo.cu), opt-in with MONKEY_B200_CONV_HALO=1.  Round-1 status: '
-                           'with descriptor base offset = (start >> 7) & 7 it ran to completion with wrong outputs (rel. error 0.8); '
-                           'the default is now base offset 0 (absolute-address swizzle, see the file header), untested; '
-                           'MONKEY_B200_HALO_BASEOFF=1 restores the first variant.')
+@pytest.mark.parametrize('kernel', ['halo', 'halo_x3'])
 @pytest.mark.parametrize('cin,cout,k,pad,H,W,N,resid,act', HALO_CASES)
-def test_conv_tc_halo_matches_fp32_kernel(cin, cout, k, pad, H, W, N, resid, act):
+def test_conv_halo_matches_torch_conv2d(cin, cout, k, pad, H, W, N, resid, act, kernel):
+    """csrc/conv_halo.cu (persistent, halo windows, resident weights, TMA-store epilogue) vs F.conv2d in double."""
     from monkey_net_b200 import lib
     torch.manual_seed(cin + cout + k)
     dev = torch.device('cuda')
@@ -264,19 +292,30 @@ def test_conv_tc_halo_matches_fp32_kernel(cin, cout, k, pad, H, W, N, resid, act
     b = torch.randn(cout, device=dev)
     Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
     r = torch.randn(N, Ho, Wo, cout, device=dev) if resid else None
-    wp, wt = torch.empty(k * k * cin * cout, device=dev), torch.empty(k * k * cin * cout, device=dev)
+    x3 = kernel == 'halo_x3'
+    wp = torch.empty(k * k * cin * cout * (2 if x3 else 1), device=dev)
     bp = torch.empty(cout, device=dev)
-    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, 0, wp.data_ptr(), b.data_ptr(),
-             bp.data_ptr(), st)
-    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, 2, wt.data_ptr(), None, None, st)
-    y0 = torch.empty(N, Ho, Wo, cout, device=dev)
-    y1 = torch.full((N, Ho, Wo, cout), float('nan'), device=dev)
-    rp = r.data_ptr() if resid else None
-    lib.call('mk_conv2d', x.data_ptr(), N, H, W, cin, cin, 0, wp.data_ptr(), k, k, pad, None, bp.data_ptr(), rp,
-             cout if resid else 0, act, 0.0, y0.data_ptr(), cout, cout, 0, st)
-    lib.call('mk_conv2d_tc_halo', x.data_ptr(), N, H, W, cin, cin, wt.data_ptr(), k, k, pad, None, bp.data_ptr(), rp,
-             cout if resid else 0, act, 0.0, y1.data_ptr(), cout, cout, st)
+    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, 2 | (8 if x3 else 0), wp.data_ptr(),
+             b.data_ptr(), bp.data_ptr(), st)
+    y = torch.full((N, Ho, Wo, cout), float('nan'), device=dev)
+    lib.call('mk_conv2d_tc_halo_x3' if x3 else 'mk_conv2d_tc_halo', x.data_ptr(), N, H, W, cin, cin, wp.data_ptr(), k, k,
+             pad, None, bp.data_ptr(), r.data_ptr() if resid else None, cout if resid else 0, act, 0.0, y.data_ptr(), cout,
+             cout, st)
     torch.cuda.synchronize()
-    assert not torch.isnan(y1).any(), 'halo kernel left outputs unwritten'
-    err = float((y0 - y1).abs().max()) / (float(y0.abs().max()) + 1e-12)
-    assert err < 2e-3, err
+    assert not torch.isnan(y).any(), 'halo kernel left outputs unwritten'
+    ref = _torch_conv(x, w, b, pad, r, act)
+    err = float((y.double() - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+    assert err < KERNEL_TOL['tf32x3' if x3 else 'tf32'], err
+
+
+def test_conv_halo_declines_small_layers_untouched():
+    """few-tile / small-image layers are left to mk_conv2d_tc: return code -2 before anything is launched"""
+    from monkey_net_b200 import lib
+    dev = torch.device('cuda')
+    x = torch.randn(2, 8, 8, 64, device=dev)
+    y = torch.zeros(2, 8, 8, 64, device=dev)
+    w = torch.zeros(9 * 64 * 64, device=dev)
+    rc = lib.call_soft('mk_conv2d_tc_halo', (-2,), x.data_ptr(), 2, 8, 8, 64, 64, w.data_ptr(), 3, 3, 1, None, None, None,
+                       0, 0, 0.0, y.data_ptr(), 64, 64, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rc == -2 and float(y.abs().max()) == 0.0
