@@ -1,17 +1,26 @@
 #!/usr/bin/env python
-"""bench.py - frames/sec of the Monkey-Net training step (BASELINE.json configs[1]: config/shapes.yaml nets, batch 32
-synthetic 64x64 frame pairs per GPU, full train.py:110-136 iteration body: G fwd+bwd + Adam(G,KP) + D fwd+bwd +
-Adam(D)) on N x B200, one process per GPU.
+"""bench.py - frames/sec of the Monkey-Net training step on N x B200, one process per GPU.
+
+Default workload (every N, weak scaling) = BASELINE.json configs[3]'s per-GPU share: config/taichi.yaml nets run at
+256x256, 8 synthetic frame pairs per GPU, the full train.py:110-136 iteration body (G fwd+bwd + Adam(G, KP) + D
+fwd+bwd + Adam(D)), data-parallel with NCCL sync-BN - at N = 8 that IS configs[3] (global batch 64).  At N = 1 the same
+line also carries, as extra objects, the other single-GPU configurations of BASELINE.json:
+  `configs1_shapes64`  configs[1]  shapes.yaml training step, 32 pairs @64x64
+  `transfer_256`       configs[2]  moving-gif.yaml nets @256x256, transfer_one 16 sources x 2 driving frames, with the
+                                   max-abs error of the timed path against the CPU oracle on the same weights / inputs
+  `voxfull_256`        configs[4]  per-GPU share: vox-full.yaml nets @256x256, 16 pairs, + grid_sample HBM GB/s
 
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the CPU restatement of the reference (oracle) on the host cores
+    python bench.py --impl reference ...      # the reference's own CPU implementation on the host cores
 
 Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs resident in HBM; `e2e` = same metric through
-the public API (DataParallelWithCallback(GeneratorFullModel)(x)) with pinned HOST inputs, H2D copy and D2H loss read
-inside the timed region; `roofline` = conv kernels' algorithmic FLOP/s vs the measured tensor peak;
-`cpu_baseline` = the oracle port timed on this box's host cores on a bounded sample of the same workload.
+the public API with pinned HOST inputs, H2D copy and D2H loss read inside the timed region; `roofline` = the
+convolution kernels' algorithmic FLOP/s vs the measured tensor peak; `cpu_baseline` = the reference's modules (from
+the byte-compiled oracle/_ref build; the oracle port when that is absent) timed on this box's host cores on a bounded
+sample of the same workload.  Training convolutions run in the 'auto' arithmetic: 3xTF32 tensor-core kernels
+(fp32-accurate); `tf32_fast` reports the same step with 1xTF32 for readers who train at TF32 like stock PyTorch.
 """
 import argparse
 import json
@@ -29,6 +38,10 @@ import torch  # noqa: E402
 import yaml  # noqa: E402
 
 METRIC = 'frames/sec (training step: G fwd+bwd+Adam, D fwd+bwd+Adam)'
+DEFAULT = {'config': 'taichi', 'res': 256, 'batch': 8}
+CONV_ENTRIES = ('mk_conv2d', 'mk_conv2d_wgrad', 'mk_conv2d_tc', 'mk_conv2d_wgrad_tc', 'mk_conv2d_tc_x3',
+                'mk_conv2d_wgrad_tc_x3', 'mk_conv2d_tc_halo', 'mk_conv2d_tc_halo_x3', 'mk_conv2d_wgrad_halo',
+                'mk_conv2d_wgrad_halo_x3')
 
 
 def parse():
@@ -37,18 +50,18 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--config', default='shapes')
-    ap.add_argument('--res', type=int, default=64)
-    ap.add_argument('--batch', type=int, default=32, help='frame pairs PER GPU (weak scaling)')
+    ap.add_argument('--config', default=DEFAULT['config'])
+    ap.add_argument('--res', type=int, default=DEFAULT['res'])
+    ap.add_argument('--batch', type=int, default=DEFAULT['batch'], help='frame pairs PER GPU (weak scaling)')
     ap.add_argument('--cpu-batch', type=int, default=None, help='batch of the CPU baseline sample')
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'],
                     help='run the iteration as one CUDA graph launch (monkey_net_b200.train_step.GraphedTrainer)')
     ap.add_argument('--workload', default='train', choices=['train', 'transfer'],
-                    help="train = configs[1] (the headline); transfer = configs[2]: moving-gif nets, 256x256, "
-                         "transfer_one on 16 sources x 2 driving frames (use --config moving-gif --res 256 --batch 16)")
-    ap.add_argument('--no-transfer', action='store_true', help='skip the 256x256 transfer side measurement')
+                    help="train = the headline; transfer = configs[2] as the bench line itself (replicas for N > 1)")
     ap.add_argument('--adam', default='flat', choices=['flat', 'torch'],
                     help='flat = monkey_net_b200.optim.FlatAdam (one fused launch per optimiser step); torch = torch.optim.Adam')
+    ap.add_argument('--no-extras', action='store_true', help='N = 1: skip configs1_shapes64 / transfer_256 / voxfull_256')
+    ap.add_argument('--no-transfer', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-bench', action='store_true')
     return ap.parse_args()
@@ -144,192 +157,262 @@ def conv_flops_per_step(cfg, res, batch):
             'train_step': batch * (3 * f_kp + 3 * f_g + 12 * f_d)}
 
 
-def run_ours(args):
-    import torch.distributed as dist
-    from monkey_net_b200 import lib, train_step
-    from sync_batchnorm import DataParallelWithCallback
+class Harness:
+    """device, process group, L2 flush and the timing rule of the contract (CUDA events per step, barrier +
+    synchronize on both sides, max over ranks)."""
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise RuntimeError('bench.py (impl=ours) needs a CUDA device; there is no CPU fallback')
-    torch.cuda.set_device(local)
-    device = torch.device('cuda', local)
-    if world > 1:
-        import datetime
-        # rendezvous of 8 cold-starting ranks can take minutes on a fresh box (first `import torch`); collectives
-        # themselves are milliseconds, so a diverged rank still fails the run well inside the driver's patience
-        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=480))
-    lib.load()
-    from monkey_net_b200 import ops as mkops
-    conv_mode = mkops.CONV_MODE
-    cfg = load_config(args.config)
-    tp = cfg['train_params']
-    gen, disc, kp = build_nets(cfg, device)
-    for m in (gen, disc, kp):
-        m.train()
-    use_graph = args.graph == 'on' or (args.graph == 'auto')
-    trainer = train_step.GraphedTrainer(kp, gen, disc, tp, use_graph=use_graph, fused_adam=(args.adam == 'flat'))
-    B = args.batch
-    torch.manual_seed(100 + rank)
-    host = {'source': torch.rand(B, 3, 1, args.res, args.res).pin_memory(),
-            'video': torch.rand(B, 3, 1, args.res, args.res).pin_memory()}
-    resident = {k: v.to(device) for k, v in host.items()}
-    flush = torch.zeros(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise RuntimeError('bench.py (impl=ours) needs a CUDA device; there is no CPU fallback')
+        torch.cuda.set_device(self.local)
+        self.device = torch.device('cuda', self.local)
+        if self.world > 1:
+            import datetime
+            # rendezvous of 8 cold-starting ranks can take minutes on a fresh box (first `import torch`)
+            dist.init_process_group('nccl', device_id=self.device, timeout=datetime.timedelta(seconds=480))
+        from monkey_net_b200 import lib
+        lib.load()
+        self.lib = lib
+        self.flush = torch.zeros(256 << 20, dtype=torch.uint8, device=self.device)  # > 126 MB L2
 
-    def barrier():
+    def barrier(self):
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        if self.world > 1:
+            self.dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(step_fn, steps):
+    def timed(self, step_fn, steps):
+        """total ms of `steps` calls, L2 flushed (write + read pass, outside the event pairs) before each"""
+        st = torch.cuda.current_stream().cuda_stream
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
+        self.barrier()
         for s, e in evs:
-            lib.call('mk_fill_zero', flush.data_ptr(), flush.numel(), torch.cuda.current_stream().cuda_stream)
-            lib.call('mk_l2_evict', flush.data_ptr(), flush.numel(), torch.cuda.current_stream().cuda_stream)
+            self.lib.call('mk_fill_zero', self.flush.data_ptr(), self.flush.numel(), st)
+            self.lib.call('mk_l2_evict', self.flush.data_ptr(), self.flush.numel(), st)
             s.record()
             step_fn()
             e.record()
-        barrier()
+        self.barrier()
         ms = sum(s.elapsed_time(e) for s, e in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([ms], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def step_resident():
-        trainer.step(resident)
 
-    last = {}
+def measure_train(h, cfg_name, res, batch, steps, warmup, adam='flat', graph=True, conv_pass=True, e2e=True,
+                  conv_mode=None, sample_clocks=False):
+    """One training workload: resident + e2e frames/s and the convolution timing pass.  Every rank runs everything
+    that contains collectives."""
+    from monkey_net_b200 import lib, train_step
+    from monkey_net_b200 import ops as mkops
+    prev_mode = mkops.CONV_MODE
+    if conv_mode:
+        mkops.set_conv_mode(conv_mode)
+    try:
+        cfg = load_config(cfg_name)
+        tp = cfg['train_params']
+        gen, disc, kp = build_nets(cfg, h.device)
+        for m in (gen, disc, kp):
+            m.train()
+        trainer = train_step.GraphedTrainer(kp, gen, disc, tp, use_graph=graph, fused_adam=(adam == 'flat'))
+        torch.manual_seed(100 + h.rank)
+        host = {'source': torch.rand(batch, 3, 1, res, res).pin_memory(),
+                'video': torch.rand(batch, 3, 1, res, res).pin_memory()}
+        resident = {k: v.to(h.device) for k, v in host.items()}
+        last = {}
 
-    def step_e2e():
-        last['loss'] = trainer.step(host).cpu()  # H2D copy of the pinned batch + step + D2H read of the losses
+        def step_resident():
+            trainer.step(resident)
 
-    for _ in range(args.warmup):
-        step_resident()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    n0 = lib.launches()
-    ms = timed(step_resident, args.steps)
-    if trainer.graph is not None:   # kernels recorded into the CUDA graph at capture time, replayed every step
-        launches = trainer.kernels_per_step * args.steps
-    else:
-        launches = lib.launches() - n0 - 2 * args.steps  # minus the L2-flush memset + read pass
-    clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+        def step_e2e():
+            last['loss'] = trainer.step(host).cpu()  # H2D copy of the pinned batch + step + D2H read of the losses
 
-    # ---- roofline of the dominant kernel family (implicit-GEMM convolutions): device time by CUDA events around
-    # every conv launch on the launching stream, algorithmic FLOPs from the oracle's conv hooks
-    conv_ms = None
-    n_conv = 0
-    if True:  # EVERY rank runs this pass: the iteration contains collectives (BN statistics, gradient all-reduce)
-        names = ('mk_conv2d', 'mk_conv2d_wgrad', 'mk_conv2d_tc', 'mk_conv2d_wgrad_tc')
-        spans = []
-        orig = lib.call
+        for _ in range(warmup):
+            step_resident()
+        sampler = ClockSampler(h.local) if sample_clocks and h.rank == 0 else None
+        if sampler:
+            sampler.start()
+        n0 = lib.launches()
+        ms = h.timed(step_resident, steps)
+        launches = trainer.kernels_per_step * steps if trainer.graph is not None else lib.launches() - n0 - 2 * steps
+        out = {'ms_per_step': ms / steps, 'value': batch * h.world * steps / (ms / 1e3), 'gpu_launches': launches,
+               'cuda_graph': trainer.graph is not None, 'conv_mode': mkops.CONV_MODE,
+               'kernels_per_step': trainer.kernels_per_step}
+        if sampler:
+            out['clocks'] = sampler.stop()
+        if e2e:
+            for _ in range(2):
+                step_e2e()
+            ms_e2e = h.timed(step_e2e, steps)
+            out['e2e'] = {'value': batch * h.world * steps / (ms_e2e / 1e3), 'unit': 'frames/s',
+                          'h2d_bytes_per_step': sum(v.numel() * 4 for v in host.values()),
+                          'd2h_bytes_per_step': int(last['loss'].numel() * 4)}
+        if conv_pass:
+            # device time of every convolution launch: CUDA events around each launch on the launching stream in an
+            # eager (ungraphed) pass; the stream is parked behind a spin so the host enqueues the whole iteration ahead
+            # of the device and every event pair brackets back-to-back device execution, not a host gap
+            spans = []
+            orig, orig_soft = lib.call, lib.call_soft
 
-        def traced(name, *a):
-            if name in names:
+            def traced(name, *a):
+                if name in CONV_ENTRIES:
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record(); orig(name, *a); e.record()
+                    spans.append((s, e))
+                else:
+                    orig(name, *a)
+
+            def traced_soft(name, soft, *a):
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record(); orig(name, *a); e.record()
-                spans.append((s, e))
-            else:
-                orig(name, *a)
-        lib.call = traced
-        from monkey_net_b200 import ops as _ops
-        _ops.lib.call = traced
-        torch.cuda.synchronize()
-        # The eager loop is CPU-bound at this size (host launch cost > kernel time): an event pair would then
-        # measure the host gap, not the kernel.  Park the stream behind a ~40 ms spin so the host enqueues the whole
-        # iteration ahead of the device; every pair then brackets back-to-back device execution.
-        torch.cuda._sleep(int(0.040 * 1.9e9))
-        trainer._iteration(resident)  # eager (ungraphed) pass so every conv launch can be bracketed by events
-        torch.cuda.synchronize()
-        lib.call = orig
-        _ops.lib.call = orig
-        conv_ms = sum(s.elapsed_time(e) for s, e in spans)
-        n_conv = len(spans)
-    if world > 1:
-        dist.barrier()
-
-    if rank != 0:
-        _exit_rank()
-    pk = peaks()
-    flops = conv_flops_per_step(cfg, args.res, B)
-    frames = B * world * args.steps
-    out = {
-        'metric': METRIC, 'value': frames / (ms / 1e3), 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None,
-        'dtype': 'tf32 tensor-core convs (fp32 accumulate), fp32 elsewhere' if conv_mode == 'tf32' else 'f32',
-        'data': 'synthetic (torch.rand frames, seeded default-init weights)',
-        'config': {'workload': 'config/%s.yaml training step, %d synthetic %dx%d frame pairs per GPU, 1 driving '
-                               'frame, fwd+bwd+Adam for G, KP and D' % (args.config, B, args.res, args.res),
-                   'global_batch': B * world, 'parallelism': 'dp%d' % world,
-                   'cuda_graph': trainer.graph is not None, 'conv_mode': conv_mode,
-                   'optimizer': 'FlatAdam (mk_adam_flat, fused zero_grad)' if args.adam == 'flat' else 'torch.optim.Adam',
-                   'l2': 'flushed between timed steps: 256 MiB memset (write) followed by a read pass over the same buffer so no dirty lines are left to be written back inside the timed region; both outside the per-step event pairs',
-                   'conv_gflop_per_sample': flops['train_step_per_sample'] / 1e9},
-        'e2e': {'value': frames / (ms_e2e / 1e3), 'unit': 'frames/s',
-                'h2d_bytes_per_step': sum(v.numel() * 4 for v in host.values()),
-                'd2h_bytes_per_step': int(last['loss'].numel() * 4)},
-        'gpu_launches': launches,
-        'clocks': clocks,
-    }
-    achieved = flops['train_step'] / (conv_ms / 1e3) / 1e12
-    out['roofline'] = {'bound': 'tensor', 'kernel': 'k_conv_tc/k_wgrad_tc (tcgen05 tf32) + k_conv_ffma/k_conv_wgrad (fp32) - implicit-GEMM conv fwd, dgrad, wgrad',
-                       'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                       'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
-                       'frac_of_tf32_peak': achieved / (pk['bf16_tflops_sustained'] / 2),
-                       'tf32_note': 'kind::tf32 issues at half the bf16 rate: the TF32 ceiling is peak/2; at 64x64 with '
-                                    '16-128 channels the convs are L2->SMEM-bandwidth bound, not tensor bound '
-                                    '(profiles/r1_ncu_conv_tc.md)',
-                       'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
-                       'launches_per_step': n_conv, 'conv_ms_per_step': conv_ms,
-                       'conv_share_of_step': conv_ms / (ms / args.steps),
-                       'note': 'conv kernels timed in an eager pass (stream parked behind a spin so launches are back to back) with CUDA events around every launch; algorithmic '
-                               'FLOPs = 3*KP2 + 3*G + 12*D conv FLOPs (2*MACs of the reference convs)'}
-    if world == 1 and not args.no_kernel_bench:
-        out['kernels'] = kernel_bench(device, pk)
-    if world == 1 and not args.no_cpu_baseline:  # 'on rank 0 at N=1 only'
-        out['cpu_baseline'] = cpu_baseline(args, cfg)
-    if world == 1 and conv_mode == 'tf32' and not args.no_kernel_bench:
-        # the same step with the EXACT fp32 (FFMA) convolutions, for readers who want the no-TF32 number
-        mkops.set_conv_mode('fp32')
-        try:
-            g2, d2, k2 = build_nets(cfg, device)
-            for m in (g2, d2, k2):
-                m.train()
-            t2 = train_step.GraphedTrainer(k2, g2, d2, tp, use_graph=use_graph)
-            for _ in range(3):
-                t2.step(resident)
-            n2 = max(3, args.steps // 2)
-            ms2 = timed(lambda: t2.step(resident), n2)
-            out['fp32_exact'] = {'value': B * n2 / (ms2 / 1e3), 'unit': 'frames/s', 'ms_per_step': ms2 / n2,
-                                 'note': 'MONKEY_B200_CONV=fp32: every convolution on the exact FFMA kernels'}
-            del t2, g2, d2, k2
-        finally:
-            mkops.set_conv_mode(conv_mode)
-    if world == 1 and not args.no_transfer:
+                s.record()
+                rc = orig_soft(name, soft, *a)
+                e.record()
+                if rc == 0 and name in CONV_ENTRIES:
+                    spans.append((s, e))
+                return rc
+            lib.call, lib.call_soft = traced, traced_soft
+            try:
+                torch.cuda.synchronize()
+                torch.cuda._sleep(int(0.060 * 1.9e9))
+                trainer._iteration(resident)
+                torch.cuda.synchronize()
+            finally:
+                lib.call, lib.call_soft = orig, orig_soft
+            out['conv_ms_per_step'] = sum(s.elapsed_time(e) for s, e in spans)
+            out['conv_launches_per_step'] = len(spans)
+        if h.world > 1:
+            h.dist.barrier()
         del trainer, gen, disc, kp
         torch.cuda.empty_cache()
-        out['transfer_256'] = transfer_bench(device, 'moving-gif', 256, 16, 2, args.steps, args.warmup,
-                                             cpu=not args.no_cpu_baseline)
+        return out
+    finally:
+        mkops.set_conv_mode(prev_mode)
+
+
+def roofline(m, flops, pk, steps_note=''):
+    achieved = flops['train_step'] / (m['conv_ms_per_step'] / 1e3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp))
+        except Exception:
+            traffic = None
+    x3 = m['conv_mode'] in ('auto', 'tf32x3')
+    return {'bound': 'tensor',
+            'kernel': 'implicit-GEMM convolutions, fwd + dgrad + wgrad: k_conv_halo / k_conv_tc / k_wgrad_tc (tcgen05 '
+                      'kind::tf32, %s)' % ('3xTF32 = three MMAs per product' if x3 else '1xTF32'),
+            'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+            'frac': achieved / pk['bf16_tflops_sustained'],
+            'traffic': traffic,
+            'frac_of_tf32_peak': achieved / (pk['bf16_tflops_sustained'] / 2),
+            'frac_of_3xtf32_ceiling': achieved / (pk['bf16_tflops_sustained'] / 6) if x3 else None,
+            'note': 'achieved = ALGORITHMIC conv FLOPs of the step (3*KP2 + 3*G + 12*D, 2*MACs of the reference convs) / '
+                    'summed device time of the conv launches (CUDA events around every launch, eager pass, stream parked '
+                    'so launches are back to back).  kind::tf32 issues at half the bf16 rate and the 3xTF32 mode spends '
+                    'three MMAs per product, so the reference-precision ceiling is peak/6; `frac` stays against the '
+                    'measured bf16 peak as the contract asks.',
+            'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
+            'launches_per_step': m['conv_launches_per_step'], 'conv_ms_per_step': m['conv_ms_per_step'],
+            'conv_share_of_step': m['conv_ms_per_step'] / m['ms_per_step']}
+
+
+def run_ours(args):
+    h = Harness()
+    from monkey_net_b200 import ops as mkops
+    use_graph = args.graph in ('on', 'auto')
+    dist_check = None
+    if h.world > 1:
+        from monkey_net_b200 import dist_check as dc
+        dist_check = dc.run(h.device)   # N ranks on shards == 1 rank on the full batch, through the kernels + NCCL
+    main = measure_train(h, args.config, args.res, args.batch, args.steps, args.warmup, adam=args.adam, graph=use_graph,
+                         sample_clocks=True)
+    if h.rank != 0:
+        _exit_rank()
+    pk = peaks()
+    cfg = load_config(args.config)
+    flops = conv_flops_per_step(cfg, args.res, args.batch)
+    mode = main['conv_mode']
+    out = {
+        'metric': METRIC, 'value': main['value'], 'unit': 'frames/s', 'n_gpus': h.world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': {'auto': 'f32 (3xTF32 tensor-core convolutions: fp32-accurate products, fp32 accumulate; fp32 elsewhere)',
+                  'tf32x3': 'f32 (3xTF32 tensor-core convolutions)', 'tf32': 'tf32 tensor-core convs (fp32 accumulate)',
+                  'fp32': 'f32 (FFMA convolutions)'}[mode],
+        'data': 'synthetic (torch.rand frames, seeded default-init weights)',
+        'config': {'workload': 'config/%s.yaml nets @%dx%d, training step (train.py:110-136: G fwd+bwd+Adam(G,KP), D '
+                               'fwd+bwd+Adam(D)), %d synthetic frame pairs per GPU%s'
+                               % (args.config, args.res, args.res, args.batch,
+                                  ' = BASELINE.json configs[3] (taichi.yaml @256, batch 64 over 8 GPUs) per-GPU share'
+                                  if (args.config, args.res, args.batch) == ('taichi', 256, 8) else ''),
+                   'global_batch': args.batch * h.world, 'parallelism': 'dp%d' % h.world,
+                   'cuda_graph': main['cuda_graph'], 'conv_mode': mode,
+                   'optimizer': 'FlatAdam (mk_adam_flat, fused zero_grad)' if args.adam == 'flat' else 'torch.optim.Adam',
+                   'l2': 'flushed between timed steps: 256 MiB memset (write) followed by a read pass over the same '
+                         'buffer so no dirty lines are written back inside the timed region; outside the event pairs',
+                   'conv_gflop_per_sample': flops['train_step_per_sample'] / 1e9},
+        'e2e': main['e2e'], 'gpu_launches': main['gpu_launches'], 'clocks': main.get('clocks'),
+        'roofline': roofline(main, flops, pk),
+    }
+    if dist_check is not None:
+        out['dist_check'] = dist_check
+    if h.world == 1:
+        if not args.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_baseline(args, cfg)
+        if not args.no_extras:
+            # the same step with every convolution 1xTF32 (what stock PyTorch/cuDNN trains with on this GPU)
+            fast = measure_train(h, args.config, args.res, args.batch, max(3, args.steps // 2), 2, conv_pass=True,
+                                 e2e=False, conv_mode='tf32', graph=use_graph)
+            out['tf32_fast'] = {'value': fast['value'], 'unit': 'frames/s', 'ms_per_step': fast['ms_per_step'],
+                                'conv_tflops': flops['train_step'] / (fast['conv_ms_per_step'] / 1e3) / 1e12,
+                                'note': 'MONKEY_B200_CONV=tf32: 1xTF32 convolutions; gradient cosine vs the fp32 oracle '
+                                        '0.94-0.98 (tests/test_gpu_3_tc.py), not the reference-precision headline'}
+            s_cfg = load_config('shapes')
+            s = measure_train(h, 'shapes', 64, 32, args.steps, args.warmup, graph=use_graph)
+            sf = conv_flops_per_step(s_cfg, 64, 32)
+            out['configs1_shapes64'] = {
+                'workload': 'BASELINE.json configs[1]: config/shapes.yaml training step, 32 synthetic 64x64 frame pairs',
+                'value': s['value'], 'unit': 'frames/s', 'ms_per_step': s['ms_per_step'], 'e2e': s['e2e'],
+                'kernels_per_step': s['kernels_per_step'], 'conv_mode': s['conv_mode'],
+                'conv_tflops': sf['train_step'] / (s['conv_ms_per_step'] / 1e3) / 1e12,
+                'conv_share_of_step': s['conv_ms_per_step'] / s['ms_per_step']}
+            if not args.no_cpu_baseline:
+                a2 = argparse.Namespace(**vars(args))
+                a2.config, a2.res, a2.batch, a2.cpu_batch = 'shapes', 64, 32, None
+                out['configs1_shapes64']['cpu_baseline'] = cpu_baseline(a2, s_cfg)
+            v = measure_train(h, 'vox-full', 256, 16, max(3, args.steps // 2), 2, graph=use_graph, e2e=False)
+            vf = conv_flops_per_step(load_config('vox-full'), 256, 16)
+            out['voxfull_256'] = {
+                'workload': 'BASELINE.json configs[4] per-GPU share: config/vox-full.yaml nets @256x256 (trilinear '
+                            'grid resize, 7-block generator), training step, 16 synthetic frame pairs',
+                'value': v['value'], 'unit': 'frames/s', 'ms_per_step': v['ms_per_step'],
+                'kernels_per_step': v['kernels_per_step'],
+                'conv_tflops': vf['train_step'] / (v['conv_ms_per_step'] / 1e3) / 1e12,
+                'conv_share_of_step': v['conv_ms_per_step'] / v['ms_per_step']}
+        if not args.no_kernel_bench:
+            out['kernels'] = kernel_bench(h.device, pk)
+            if 'voxfull_256' in out:
+                out['voxfull_256']['grid_sample'] = out['kernels']
+        if not args.no_transfer and not args.no_extras:
+            out['transfer_256'] = transfer_bench(h.device, 'moving-gif', 256, 16, 2, args.steps, args.warmup,
+                                                 cpu=not args.no_cpu_baseline)
     print(json.dumps(out))
-    if world > 1:
+    if h.world > 1:
         _exit_rank()
 
 
 def _exit_rank():
-    """Multi-rank exit without NCCL teardown ordering: rank 0 goes on to CPU-side work (FLOP count, CPU baseline) for
-    up to a minute after the other ranks are done, and ncclCommDestroy on one side waiting for a peer that has already
-    left hung the launcher (observed at N=2).  All collectives are complete and synchronised at this point, so the
-    processes flush and leave; the driver reads rank 0's JSON line."""
+    """Multi-rank exit without NCCL teardown ordering: rank 0 goes on to CPU-side work (FLOP count) after the other
+    ranks are done, and ncclCommDestroy on one side waiting for a peer that has already left hung the launcher
+    (observed at N=2).  All collectives are complete and synchronised at this point, so the processes flush and leave;
+    the driver reads rank 0's JSON line."""
     sys.stdout.flush()
     sys.stderr.flush()
     os._exit(0)
@@ -339,12 +422,14 @@ def transfer_bench(device, config, res, batch, d, steps, warmup, cpu=True):
     """BASELINE.json configs[2] / north-star 256x256 transfer: `config` nets at res x res, eval mode, transfer_one
     (transfer.py:65-79) on `batch` sources x `d` driving frames = batch*d generated frames per call.  `value`: inputs
     resident in HBM; `e2e`: pinned host inputs -> H2D -> graph -> D2H of the predicted frames (what transfer.py:116
-    does with `.data.cpu().numpy()`); `cpu_baseline`: the oracle's transfer_one on a bounded sample."""
+    does with `.data.cpu().numpy()`); `parity`: the TIMED path's frames / keypoints against the CPU oracle loaded with
+    the same weights on the first 2 sources; `cpu_baseline`: the reference's transfer_one on a bounded sample."""
     from monkey_net_b200 import lib, transfer_step
     from monkey_net_b200 import ops as mkops
     cfg = load_config(config)
     gen, disc, kp = build_nets(cfg, device)
     del disc
+    torch.manual_seed(7)
     x = {'source': torch.rand(batch, 3, 1, res, res), 'driving': torch.rand(batch, 3, d, res, res)}
     with torch.no_grad():  # populate the BN running statistics the way a trained checkpoint would carry them
         for m in (gen, kp):
@@ -371,7 +456,7 @@ def transfer_bench(device, config, res, batch, d, steps, warmup, cpu=True):
         return sum(a.elapsed_time(b) for a, b in evs) / n
 
     def call_resident():
-        runner.run(resident['source'], resident['driving'])
+        return runner.run(resident['source'], resident['driving'])
 
     def call_e2e():
         o = runner.run(host['source'], host['driving'])
@@ -383,13 +468,35 @@ def transfer_bench(device, config, res, batch, d, steps, warmup, cpu=True):
     call_e2e()
     ms_e2e = timed(call_e2e, steps)
     frames = batch * d
-    r = {'workload': 'config/%s.yaml nets @%dx%d, eval, transfer_one: %d sources x %d driving frames per call, CUDA '
-                     'graph, all driving frames batched into one KP + one generator pass' % (config, res, res, batch, d),
+    r = {'workload': 'BASELINE.json configs[2]: config/%s.yaml nets @%dx%d, eval, transfer_one: %d sources x %d driving '
+                     'frames per call, CUDA graph, all driving frames batched into one KP + one generator pass'
+                     % (config, res, res, batch, d),
          'metric': 'generated frames/sec (transfer)', 'value': frames / (ms / 1e3), 'unit': 'frames/s',
          'ms_per_call': ms, 'conv_mode': mkops.CONV_MODE, 'kernels_per_call': runner.kernels_per_call,
          'e2e': {'value': frames / (ms_e2e / 1e3), 'unit': 'frames/s',
                  'h2d_bytes_per_step': sum(v.numel() * 4 for v in host.values()),
                  'd2h_bytes_per_step': out_host.numel() * 4}}
+    # ---- parity of THIS path (graph replay, fused inference kernels) against the CPU oracle, same weights, same inputs
+    try:
+        from oracle import monkey_oracle as mo
+        og, od, ok = mo.build_from_config(cfg)
+        og.load_state_dict({k: v.cpu() for k, v in gen.state_dict().items()})
+        ok.load_state_dict({k: v.cpu() for k, v in kp.state_dict().items()})
+        for m in (og, ok):
+            m.eval()
+        got = call_resident()
+        with torch.no_grad():
+            want = mo.transfer_one(og, ok, x['source'][:2], x['driving'][:2], tparams['normalization_params'])
+        g_mean = got['kp_driving']['mean'][:2].cpu()
+        px = lambda m_: torch.round(res * (m_ + 1) / 2)
+        r['parity'] = {
+            'frames_max_abs': float((got['video_prediction'][:2].cpu() - want['video_prediction']).abs().max()),
+            'kp_mean_max_abs': float((g_mean - want['kp_driving']['mean']).abs().max()),
+            'kp_pixel_indices_identical': bool(torch.equal(px(g_mean), px(want['kp_driving']['mean']))),
+            'note': 'timed path vs oracle/monkey_oracle.py (CPU fp32) with the same state_dict on sources 0-1, all %d '
+                    'driving frames; north-star bar 1e-3 on the frames, identical keypoint pixel indices' % d}
+    except Exception as ex:  # the checker must never take the measurement down
+        r['parity'] = {'error': repr(ex)}
     if cpu:
         r['cpu_baseline'] = cpu_transfer_baseline(cfg, config, res, 2, d)
         r['e2e_speedup_vs_cpu'] = r['e2e']['value'] / r['cpu_baseline']['value']
@@ -398,12 +505,33 @@ def transfer_bench(device, config, res, batch, d, steps, warmup, cpu=True):
     return r
 
 
+def _reference_or_port(cfg):
+    """(generator, discriminator, kp_detector, kind, module namespace): the reference's OWN modules from the
+    byte-compiled oracle/_ref build (or the source tree in the build container) when present - cpu_baseline.kind
+    'reference' - else the oracle port."""
+    from oracle import monkey_oracle as mo
+    try:
+        from oracle import ref_shim
+        if ref_shim.available():
+            rg, rd, rk = ref_shim.build_from_config(cfg)
+            return rg, rd, rk, 'reference', ref_shim
+    except Exception:
+        pass
+    og, od, ok = mo.build_from_config(cfg)
+    return og, od, ok, 'port', None
+
+
 def cpu_transfer_baseline(cfg, config, res, batch, d):
     from oracle import monkey_oracle as mo
-    og, od, ok = mo.build_from_config(cfg)
     torch.manual_seed(0)
+    og, od, ok, kind, shim = _reference_or_port(cfg)
     for m in (og, ok):
         m.eval()
+    if kind == 'reference':
+        tmod = shim.load_driver('transfer', modules='reference')
+        run = lambda s, v, norm: tmod.transfer_one(og, ok, s, v, {'normalization_params': norm})
+    else:
+        run = lambda s, v, norm: mo.transfer_one(og, ok, s, v, norm)
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
     x = {'source': torch.rand(batch, 3, 1, res, res), 'driving': torch.rand(batch, 3, d, res, res)}
     norm = cfg['transfer_params']['normalization_params']
@@ -412,9 +540,9 @@ def cpu_transfer_baseline(cfg, config, res, batch, d):
     for c in sorted({c for c in (16, 32, 64, ncpu) if c <= ncpu}):
         torch.set_num_threads(c)
         with torch.no_grad():
-            mo.transfer_one(og, ok, x['source'], x['driving'], norm)  # warm-up (oneDNN primitive creation)
+            run(x['source'], x['driving'], norm)  # warm-up (oneDNN primitive creation)
             t0 = time.perf_counter()
-            mo.transfer_one(og, ok, x['source'], x['driving'], norm)
+            run(x['source'], x['driving'], norm)
             t = time.perf_counter() - t0
         probe[c] = round(batch * d / t, 2)
         if best is None or t < best[1]:
@@ -424,13 +552,14 @@ def cpu_transfer_baseline(cfg, config, res, batch, d):
     with torch.no_grad():
         for _ in range(3):
             t0 = time.perf_counter()
-            mo.transfer_one(og, ok, x['source'], x['driving'], norm)
+            run(x['source'], x['driving'], norm)
             ts.append(time.perf_counter() - t0)
     ts.sort()
-    return {'value': batch * d / ts[1], 'unit': 'frames/s', 'cores': best[0], 'kind': 'port',
-            'sample': 'oracle transfer_one (per-frame loop of transfer.py:65-79), %s.yaml @%dx%d, %d sources x %d '
-                      'driving frames, median of 3 after warm-up; %d of %d host threads (fastest of %s)'
-                      % (config, res, res, batch, d, best[0], ncpu, probe)}
+    return {'value': batch * d / ts[1], 'unit': 'frames/s', 'cores': best[0], 'kind': kind,
+            'sample': '%s transfer_one (per-frame loop of transfer.py:65-79), %s.yaml @%dx%d, %d sources x %d driving '
+                      'frames, median of 3 after warm-up; %d of %d host threads (fastest of %s)'
+                      % ("the reference's own transfer.py + modules (oracle/_ref)" if kind == 'reference' else 'oracle port',
+                         config, res, res, batch, d, best[0], ncpu, probe)}
 
 
 def kernel_bench(device, pk):
@@ -469,36 +598,53 @@ def kernel_bench(device, pk):
 
 
 # ------------------------------------------------------------------------------------------------- CPU arms
-def oracle_step_time(cfg, res, batch, steps, warmup):
+def cpu_step_time(cfg, res, batch, steps, warmup):
+    """median seconds of one training iteration on the host CPU: the reference's own train.py FullModels + modules
+    (oracle/_ref) when available, else the oracle port; returns (seconds, kind)."""
     from oracle import monkey_oracle as mo
-    from modules.generator import MotionTransferGenerator
-    from modules.discriminator import Discriminator
-    from modules.keypoint_detector import KPDetector
     mp, tp = cfg['model_params'], cfg['train_params']
     torch.manual_seed(0)
-    pg = MotionTransferGenerator(**mp['generator_params'], **mp['common_params'])
-    pd = Discriminator(**mp['discriminator_params'], **mp['common_params'])
-    pk = KPDetector(**mp['kp_detector_params'], **mp['common_params'])
-    og, od, ok = mo.build_from_config(cfg)
-    og.load_state_dict(pg.state_dict()); od.load_state_dict(pd.state_dict()); ok.load_state_dict(pk.state_dict())
+    og, od, ok, kind, shim = _reference_or_port(cfg)
     with torch.no_grad():
         g = torch.Generator().manual_seed(1)
         w = og.dense_motion_module.hourglass.decoder.conv.weight
         w.copy_(torch.randn(w.shape, generator=g) * 0.05)
     for m in (og, od, ok):
         m.train()
-    opts = mo.make_optimizers(og, od, ok, tp['lr'])
     torch.manual_seed(100)
     x = {'source': torch.rand(batch, 3, 1, res, res), 'video': torch.rand(batch, 3, 1, res, res)}
+    if kind == 'reference':
+        tr = shim.load_driver('train', modules='reference')
+        g_full = tr.GeneratorFullModel(ok, og, od, tp)
+        d_full = tr.DiscriminatorFullModel(ok, og, od, tp)
+        mk = lambda m: torch.optim.Adam(m.parameters(), lr=tp['lr'], betas=(0.5, 0.999))
+        o_g, o_d, o_k = mk(og), mk(od), mk(ok)
+
+        def iteration():   # train.py:110-136, the loop body verbatim (logging excluded)
+            out = g_full(x)
+            loss_values = [val.mean() for val in out[:-2]]
+            generated, kp_joined = out[-2], out[-1]
+            sum(loss_values).backward(retain_graph=not tp['detach_kp_discriminator'])
+            o_g.step(); o_g.zero_grad(); o_d.zero_grad()
+            if tp['detach_kp_discriminator']:
+                o_k.step(); o_k.zero_grad()
+            loss_values = [val.mean() for val in d_full(x, kp_joined, generated)]
+            sum(loss_values).backward()
+            o_d.step(); o_d.zero_grad()
+            if not tp['detach_kp_discriminator']:
+                o_k.step(); o_k.zero_grad()
+    else:
+        opts = mo.make_optimizers(og, od, ok, tp['lr'])
+        iteration = lambda: mo.train_iteration(ok, og, od, opts, tp, x)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        mo.train_iteration(ok, og, od, opts, tp, x)
+        iteration()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     times.sort()
-    return times[len(times) // 2]
+    return times[len(times) // 2], kind
 
 
 def pick_threads(cfg, res):
@@ -506,52 +652,53 @@ def pick_threads(cfg, res):
     oneDNN slower, e.g. 128 threads on 64x64 frames): probe a few counts on a small batch, keep the best."""
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
     cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    pb = 4 if res <= 64 else 1
     best, probe = None, {}
     for c in cands:
         torch.set_num_threads(c)
-        t = oracle_step_time(cfg, res, 4, steps=1, warmup=1)
-        probe[c] = round(4 / t, 2)
+        t, _ = cpu_step_time(cfg, res, pb, steps=1, warmup=1)
+        probe[c] = round(pb / t, 2)
         if best is None or t < best[1]:
             best = (c, t)
         if t > 4 * best[1]:
             break
     torch.set_num_threads(best[0])
-    return best[0], probe, ncpu
+    return best[0], probe, ncpu, pb
 
 
-def cpu_baseline(args, cfg):
-    threads, probe, ncpu = pick_threads(cfg, args.res)
+def cpu_baseline(args, cfg, steps=5, warmup=2):
+    threads, probe, ncpu, pb = pick_threads(cfg, args.res)
     b = args.cpu_batch or (args.batch if args.res <= 64 else 2)
-    t = oracle_step_time(cfg, args.res, b, steps=5, warmup=2)
-    return {'value': b / t, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-            'sample': 'oracle/monkey_oracle.py (plain-PyTorch CPU restatement of the reference step), %s.yaml, '
-                      'batch %d @%dx%d, median of 5 steps after 2 warm-up; %d of %d host threads (fastest of the '
-                      'probed counts, frames/s at batch 4: %s)' % (args.config, b, args.res, args.res, threads, ncpu,
-                                                                   probe)}
+    if args.res > 64:
+        steps, warmup = min(steps, 3), 1
+    t, kind = cpu_step_time(cfg, args.res, b, steps=steps, warmup=warmup)
+    what = "the reference's own train.py FullModels + modules (byte-compiled oracle/_ref), unmodified" \
+        if kind == 'reference' else 'oracle/monkey_oracle.py (plain-PyTorch CPU restatement of the reference step)'
+    return {'value': b / t, 'unit': 'frames/s', 'cores': threads, 'kind': kind,
+            'sample': '%s, %s.yaml, batch %d @%dx%d, median of %d steps after %d warm-up; %d of %d host threads (fastest '
+                      'of the probed counts, frames/s at batch %d: %s)'
+                      % (what, args.config, b, args.res, args.res, steps, warmup, threads, ncpu, pb, probe)}
 
 
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path = the pinned oracle port (the reference itself
-    cannot travel to the GPU box and has no installable package), all host threads, bounded sample per step."""
+    """Reference arm: the reference's CPU implementation of the path on the host cores - its own modules and train.py
+    FullModels from the byte-compiled oracle/_ref build (cpu_baseline.kind 'reference'), the pinned oracle port when
+    that build is absent - all useful host threads, bounded sample per step."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cfg = load_config(args.config)
-    threads, probe, ncpu = pick_threads(cfg, args.res)
+    steps, warm = max(1, min(args.steps, 5 if args.res <= 64 else 3)), max(1, min(args.warmup, 2 if args.res <= 64 else 1))
+    cb = cpu_baseline(args, cfg, steps=steps, warmup=warm)
+    val = cb['value']
     b = args.cpu_batch or (args.batch if args.res <= 64 else 2)
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    t = oracle_step_time(cfg, args.res, b, steps=steps, warmup=warm)
-    val = b / t
-    cb = {'value': val, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-          'sample': 'oracle port, %s.yaml, batch %d @%dx%d, median of %d steps; %d of %d host threads (fastest of '
-                    'the probed counts, frames/s at batch 4: %s)' % (args.config, b, args.res, args.res, steps, threads,
-                                                                     ncpu, probe)}
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'frames/s', 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': warm, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'steps': steps, 'warmup': warm, 'ms_per_step': b / val * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'config/%s.yaml training step, CPU, batch %d @%dx%d' % (args.config, b, args.res,
-                                                                                        args.res)},
+        'config': {'workload': 'config/%s.yaml training step on the host CPU, batch %d @%dx%d (bounded sample of the '
+                               'GPU arm\'s workload; CPU cost per frame is flat in the batch)'
+                               % (args.config, b, args.res, args.res)},
         'cpu_baseline': cb,
         'e2e': {'value': val, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
@@ -563,9 +710,9 @@ def run_transfer(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    cfgname = args.config if args.config != 'shapes' else 'moving-gif'
-    res = args.res if args.res != 64 else 256
-    batch = args.batch if args.batch != 32 else 16
+    cfgname = args.config if args.config != DEFAULT['config'] else 'moving-gif'
+    res = args.res
+    batch = args.batch if args.batch != DEFAULT['batch'] else 16
     if args.impl == 'reference':
         if rank == 0:
             cb = cpu_transfer_baseline(load_config(cfgname), cfgname, res, 2, 2)
@@ -596,12 +743,12 @@ def run_transfer(args):
         out = {'metric': r['metric'], 'value': frames / (float(t[0]) / 1e3), 'unit': 'frames/s', 'n_gpus': world,
                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(t[0]), 'higher_is_better': True,
                'scaling': 'weak', 'vs_baseline': None,
-               'dtype': 'tf32 tensor-core convs (fp32 accumulate), fp32 elsewhere' if r['conv_mode'] == 'tf32' else 'f32',
+               'dtype': 'geometry networks 3xTF32, appearance path 1xTF32 tensor-core convs (fp32 accumulate)',
                'data': 'synthetic (torch.rand frames, seeded default-init weights)',
                'config': {'workload': r['workload'], 'parallelism': 'replicas x%d' % world,
                           'l2': 'flushed between timed calls'},
                'e2e': dict(r['e2e'], value=frames / (float(t[1]) / 1e3)),
-               'gpu_launches': r['kernels_per_call'] * args.steps, 'clocks': clocks}
+               'gpu_launches': r['kernels_per_call'] * args.steps, 'clocks': clocks, 'parity': r.get('parity')}
         if 'cpu_baseline' in r:
             out['cpu_baseline'] = r['cpu_baseline']
         print(json.dumps(out))

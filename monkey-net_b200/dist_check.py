@@ -1,0 +1,170 @@
+"""On-GPU data-parallel invariant: N ranks on batch shards == 1 rank on the concatenated batch.
+
+Runs through the REAL path - the CUDA kernels of this library, NCCL all-reduces of the packed BN statistics in forward
+and backward, averaged parameter gradients - not a restatement of the math:
+
+  * every rank builds the same small nets (seeded) and the same GLOBAL batch of 2 x world samples;
+  * "sharded": train-mode G-step forward + backward on THIS rank's contiguous shard with sync-BN on, parameter
+    gradients averaged over ranks (one flat all-reduce, what FlatAdam.sync_gradients does);
+  * "full": the same nets (fresh copy of the weights) on the WHOLE batch with sync-BN off, on this rank alone;
+  * compared: the generator's prediction and keypoints on the shard's samples, the per-sample loss terms, the BN
+    running statistics after the step and every parameter gradient (cosine + relative error).
+
+`bench.py --gpus N` runs it as a pre-flight and reports the result under `dist_check`; tests/test_gpu_7_dist.py spawns
+it on 2 GPUs.  Replaces the reference's thread-rendezvous master/slave reduction (sync_batchnorm/batchnorm.py:90-125,
+sync_batchnorm/comm.py) - deviation noted in DESIGN.md: single-device F.batch_norm semantics on the global batch.
+"""
+import copy
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tiny_cfg():
+    import yaml
+    cfg = yaml.safe_load(open(os.path.join(ROOT, 'config', 'taichi.yaml')))
+    mp = cfg['model_params']
+    mp['common_params']['num_kp'] = 3
+    mp['kp_detector_params'].update(block_expansion=8, max_features=32, num_blocks=2)
+    g = mp['generator_params']
+    g.update(block_expansion=8, max_features=32, num_blocks=2, num_refinement_blocks=1)
+    g['dense_motion_params'].update(block_expansion=8, max_features=32, num_blocks=2)
+    mp['discriminator_params'].update(block_expansion=8, max_features=32, num_blocks=2)
+    cfg['train_params']['loss_weights']['reconstruction'] = [10, 10, 1]
+    return cfg
+
+
+def _frames(b, res, seed):
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, res), torch.linspace(-1, 1, res), indexing='ij')
+    out = torch.zeros(b, 3, 1, res, res)
+    for i in range(b):
+        for c in range(3):
+            acc = torch.full_like(xx, 0.5)
+            for _ in range(4):
+                r = torch.rand(4, generator=g)
+                cx, cy = r[0].item() * 1.6 - 0.8, r[1].item() * 1.6 - 0.8
+                s, a = 0.15 + 0.5 * r[2].item(), 0.8 * r[3].item() - 0.4
+                acc = acc + a * torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+            out[i, c, 0] = acc.clamp(0, 1)
+    return out
+
+
+def _build(cfg, device):
+    from modules.generator import MotionTransferGenerator
+    from modules.discriminator import Discriminator
+    from modules.keypoint_detector import KPDetector
+    mp = cfg['model_params']
+    torch.manual_seed(0)
+    gen = MotionTransferGenerator(**mp['generator_params'], **mp['common_params'])
+    disc = Discriminator(**mp['discriminator_params'], **mp['common_params'])
+    kp = KPDetector(**mp['kp_detector_params'], **mp['common_params'])
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(1)
+        w = gen.dense_motion_module.hourglass.decoder.conv.weight
+        w.copy_(torch.randn(w.shape, generator=g) * 0.05)
+    return gen.to(device), disc.to(device), kp.to(device)
+
+
+def run(device, res=64, per_rank=2):
+    """Returns a JSON-able dict; every rank must call it (it contains collectives)."""
+    from . import dist as mkdist
+    from .train_step import GeneratorFullModel
+    world = mkdist.world()
+    rank = mkdist.rank()
+    cfg = _tiny_cfg()
+    tp = cfg['train_params']
+    gb = per_rank * world
+    x = {'source': _frames(gb, res, 11).to(device), 'video': _frames(gb, res, 12).to(device)}
+    nets_s = _build(cfg, device)
+    nets_f = tuple(copy.deepcopy(m) for m in nets_s)
+    for m in nets_s + nets_f:
+        m.train()
+
+    def step(nets, batch):
+        gen, disc, kp = nets
+        out = GeneratorFullModel(kp, gen, disc, tp)(batch)
+        sum(v.mean() for v in out[:-2]).backward()
+        return out
+
+    lo, hi = rank * per_rank, (rank + 1) * per_rank
+    mkdist.set_sync_bn(True)
+    out_s = step(nets_s, {k: v[lo:hi] for k, v in x.items()})
+    grads_s = [p.grad for m in nets_s[:1] + nets_s[2:] for p in m.parameters() if p.grad is not None]
+    if world > 1:
+        flat = torch.cat([g.reshape(-1) for g in grads_s])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+        off = 0
+        for g in grads_s:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+    mkdist.set_sync_bn(False)
+    try:
+        out_f = step(nets_f, x)
+    finally:
+        mkdist.set_sync_bn(True)
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+    rep = {'world': world, 'global_batch': gb, 'res': res}
+    rep['prediction_max_abs'] = float((out_s[-2]['video_prediction'] - out_f[-2]['video_prediction'][lo:hi]).abs().max())
+    rep['kp_mean_max_abs'] = float((out_s[-1]['mean'] - out_f[-1]['mean'][lo:hi]).abs().max())
+    rep['loss_terms_rel'] = max(rel(a, b[lo:hi]) for a, b in zip(out_s[:-2], out_f[:-2]))
+    bn_s = [b for m in nets_s for n, b in m.named_buffers() if n.endswith('running_var') or n.endswith('running_mean')]
+    bn_f = [b for m in nets_f for n, b in m.named_buffers() if n.endswith('running_var') or n.endswith('running_mean')]
+    rep['bn_running_stats_rel'] = max(rel(a, b) for a, b in zip(bn_s, bn_f))
+    coss, rels = [], []
+    names = [n for m in nets_s[:1] + nets_s[2:] for n, p in m.named_parameters() if p.grad is not None]
+    grads_f = [p.grad for m in nets_f[:1] + nets_f[2:] for p in m.parameters() if p.grad is not None]
+    for n, a, b in zip(names, grads_s, grads_f):
+        if float(b.norm()) < 1e-7:   # structurally zero gradients (conv bias in front of a norm): rounding noise
+            continue
+        coss.append(float(torch.dot(a.flatten(), b.flatten()) / (a.norm() * b.norm() + 1e-30)))
+        rels.append(rel(a, b))
+    coss.sort(); rels.sort()
+    rep['grad_cosine_min'] = coss[0]
+    rep['grad_cosine_median'] = coss[len(coss) // 2]
+    rep['grad_rel_median'] = rels[len(rels) // 2]
+    rep['grad_rel_max'] = rels[-1]
+    t = torch.tensor([rep['prediction_max_abs'], rep['kp_mean_max_abs'], rep['loss_terms_rel'],
+                      rep['bn_running_stats_rel'], -rep['grad_cosine_min'], -rep['grad_cosine_median'],
+                      rep['grad_rel_median'], rep['grad_rel_max']], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)   # worst rank
+    (rep['prediction_max_abs'], rep['kp_mean_max_abs'], rep['loss_terms_rel'], rep['bn_running_stats_rel'], c0, c1,
+     rep['grad_rel_median'], rep['grad_rel_max']) = [float(v) for v in t.tolist()]
+    rep['grad_cosine_min'], rep['grad_cosine_median'] = -c0, -c1
+    rep['ok'] = bool(rep['prediction_max_abs'] < 1e-4 and rep['kp_mean_max_abs'] < 1e-5 and
+                     rep['loss_terms_rel'] < 1e-4 and rep['bn_running_stats_rel'] < 1e-5 and
+                     rep['grad_cosine_median'] > 0.9999 and rep['grad_cosine_min'] > 0.99)
+    rep['invariant'] = 'N ranks on contiguous shards (NCCL sync-BN fwd+bwd, averaged gradients) == one rank on the full batch'
+    return rep
+
+
+def main():
+    """torchrun entry: python -m torch.distributed.run --nproc-per-node N monkey-net_b200/dist_check.py"""
+    import datetime
+    import json
+    sys.path.insert(0, ROOT)
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=300))
+    import monkey_net_b200.dist_check as me
+    rep = me.run(device)
+    if int(os.environ.get('RANK', '0')) == 0:
+        print('DIST_CHECK ' + json.dumps(rep))
+    sys.stdout.flush()
+    os._exit(0 if rep['ok'] else 3)
+
+
+if __name__ == '__main__':
+    main()

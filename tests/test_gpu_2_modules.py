@@ -90,10 +90,12 @@ def test_forward_parity_configs(name, res):
         assert helpers.max_abs(ga['video_deformed'], oa['video_deformed']) < 1e-3
         kd1 = {k: v[:, :1] for k, v in b.items()}
         om = od(x['video'][:, :, :1], kd1, ks)
-        gm = disc(x['video'][:, :, :1].cuda(), {k: v.cuda() for k, v in kd1.items()}, ksc)
-        for p, q in zip(gm, om):
-            assert p.shape == q.shape
-            assert helpers.max_abs(p, q) < 1e-3 * max(1.0, float(q.abs().max()))
+    # the discriminator only ever runs inside the training step, i.e. with autograd recording (train.py:44-45,71-72):
+    # evaluate it the way the product runs it (reference-precision convolutions under the 'auto' policy)
+    gm = disc(x['video'][:, :, :1].cuda(), {k: v.cuda() for k, v in kd1.items()}, ksc)
+    for p, q in zip(gm, om):
+        assert p.shape == q.shape
+        assert helpers.max_abs(p, q) < 1e-3 * max(1.0, float(q.abs().max()))
 
 
 def test_train_step_gradient_parity_tiny():

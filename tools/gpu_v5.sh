@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_3_tc.py -k "halo" -q --tb=short --timeout 120 -p no:cacheprovider -x 2>&1 | tail -30 > gpurun_out/halo_tests.log
+tail -3 gpurun_out/halo_tests.log
+if grep -q "passed" gpurun_out/halo_tests.log && ! grep -q "failed" gpurun_out/halo_tests.log; then
+  timeout 400 python tools/conv_micro.py > gpurun_out/conv_micro.txt 2>&1
+  cat gpurun_out/conv_micro.txt
+  timeout 300 python -m pytest tests/test_gpu_2_modules.py -q --tb=long --timeout 300 -p no:cacheprovider -x -k "golden_tiny or forward_parity" 2>&1 | tail -80 > gpurun_out/tests_g2.log
+  tail -40 gpurun_out/tests_g2.log
+fi
