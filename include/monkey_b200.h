@@ -132,6 +132,19 @@ int mk_conv2d_wgrad(const float* x, int N, int Hin, int Win, int Cin_p, int ldx,
  * layout as mk_conv2d_wgrad.  Channel counts must be multiples of 4; returns -2 otherwise. */
 int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
                        int ldy, int R, int S, int pad, float* dwpack, void* stream);
+/* Halo-window tensor-core weight gradient (csrc/wgrad_halo.cu), the default for 3x3 / 4x4 layers with enough pixels:
+ * the X halo of a pixel tile is loaded once per 32-channel chunk and every filter tap is a row-shifted window of it; the
+ * tap ROWS ride on the MMA's M dimension (four 32-channel blocks one image row apart, descriptor leading-dimension
+ * offset), so D[32 r + ci][co] = dW[(r, s)][ci][co] and N = co is as narrow as the layer.  Same output layout as
+ * mk_conv2d_wgrad.  Returns -2 (nothing touched) outside its envelope - callers then use mk_conv2d_wgrad_tc.  _x3 =
+ * 3xTF32 (both operands split hi / lo in shared memory). */
+int mk_conv2d_wgrad_halo(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
+                         int ldy, int R, int S, int pad, float* dwpack, void* stream);
+int mk_conv2d_wgrad_halo_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
+                            int ldy, int R, int S, int pad, float* dwpack, void* stream);
+/* dry run: out[16] = co tiles, ci groups, pixel splits, smem bytes, stages, tile rows, ci chunks per CTA, dY boxes, TMEM
+ * columns, tiles, tiles per split, UMMA N, stage bytes, x3, valid tile width, tile rows of the image */
+int mk_conv2d_wgrad_halo_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int R, int S, int pad, int x3, int* out);
 /* 3xTF32 variant (see mk_conv2d_tc_x3): both operand tiles are split hi + lo in shared memory. */
 int mk_conv2d_wgrad_tc_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
                           int ldy, int R, int S, int pad, float* dwpack, void* stream);

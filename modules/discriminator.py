@@ -22,7 +22,7 @@ class DownBlock3D(nn.Module):
             self.norm = None
 
     def run(self, a):
-        y = ops.conv(a, self.conv.weight, self.conv.bias, pad=0)
+        y = ops.conv(a, self.conv.weight, self.conv.bias, pad=0, feeds_train_norm=self.norm is not None)
         return ops.norm_act(y, self.norm, mode='in' if self.norm is not None else 'none', slope=0.2, pool=1)
 
     def forward(self, x):

@@ -95,7 +95,7 @@ class ResBlock3D(_Block):
     def run(self, a):
         a = ops.compact(a)
         t = ops.norm_act(a, self.norm1, mode='bn', slope=0.0)
-        t = ops.conv(t, self.conv1.weight, self.conv1.bias, pad=self.pad)
+        t = ops.conv(t, self.conv1.weight, self.conv1.bias, pad=self.pad, feeds_train_norm=bool(self.norm2.training))
         t = ops.norm_act(t, self.norm2, mode='bn', slope=0.0)
         return ops.conv(t, self.conv2.weight, self.conv2.bias, pad=self.pad, resid=a)
 

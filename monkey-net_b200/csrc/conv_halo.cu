@@ -77,6 +77,61 @@ __device__ __forceinline__ void umma_lh(uint32_t tmem_d, uint32_t alo, uint32_t 
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
 
+// One chunk's MMAs for one row-block with RESIDENT weights, fully unrolled over taps and K steps (NK compile-time):
+// per MMA two 64-bit uniform adds + one UTCHMMA, no predicates, no loop-carried vector registers.
+template <int R, int S, bool X3, int NK>
+__device__ __forceinline__ void issue_taps_resident(uint32_t d, uint64_t ad, uint64_t bd, uint64_t a_half16,
+                                                    uint64_t b_half16, uint64_t b_slot16, uint32_t idesc,
+                                                    uint32_t acc_first) {
+#pragma unroll
+    for (int tap = 0; tap < R * S; ++tap) {
+        const uint64_t a = ad + (uint64_t)(((tap / S) * 16 + (tap % S)) * 8);   // row-shifted window, 16-byte units
+        const uint64_t b = bd + (uint64_t)tap * b_slot16;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            const uint32_t acc = (tap | k) ? 1u : acc_first;
+            if (X3) {
+                umma_tf32(d, a + a_half16 + 2 * k, b + 2 * k, idesc, acc);
+                umma_tf32(d, a + 2 * k, b + b_half16 + 2 * k, idesc, 1u);
+                umma_tf32(d, a + 2 * k, b + 2 * k, idesc, 1u);
+            } else {
+                umma_tf32(d, a + 2 * k, b + 2 * k, idesc, acc);
+            }
+        }
+    }
+}
+
+// Streaming weights: tap-major (one weight slot feeds every row-block before it is released).
+template <int R, int S, bool X3, int NK>
+__device__ __forceinline__ void issue_taps_streaming(uint32_t dbase, int RB, int npad, uint64_t a_desc, uint64_t b_desc0,
+                                                     uint64_t a_half16, uint64_t b_half16, uint64_t b_slot16,
+                                                     uint32_t idesc, uint32_t acc_first, uint64_t* b_full,
+                                                     uint64_t* b_empty, int& bs, uint32_t& bphase, int b_slots) {
+#pragma unroll
+    for (int tap = 0; tap < R * S; ++tap) {
+        mbar_wait(&b_full[bs], bphase);
+        const uint64_t b = b_desc0 + (uint64_t)bs * b_slot16;
+        uint64_t a = a_desc + (uint64_t)(((tap / S) * 16 + (tap % S)) * 8);
+        uint32_t d = dbase;
+#pragma unroll 1
+        for (int rb = 0; rb < RB; ++rb, a += 1024, d += (uint32_t)npad) {   // next row-block: + 8 image rows = 16 KB
+#pragma unroll
+            for (int k = 0; k < NK; ++k) {
+                const uint32_t acc = (tap | k) ? 1u : acc_first;
+                if (X3) {
+                    umma_tf32(d, a + a_half16 + 2 * k, b + 2 * k, idesc, acc);
+                    umma_tf32(d, a + 2 * k, b + b_half16 + 2 * k, idesc, 1u);
+                    umma_tf32(d, a + 2 * k, b + 2 * k, idesc, 1u);
+                } else {
+                    umma_tf32(d, a + 2 * k, b + 2 * k, idesc, acc);
+                }
+            }
+        }
+        umma_commit(&b_empty[bs]);
+        if (++bs == b_slots) { bs = 0; bphase ^= 1; }
+    }
+}
+
 template <int R, int S, bool X3, bool RES>
 __global__ void __launch_bounds__(H_THREADS, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -166,11 +221,13 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else if (warp == 8) {
         // ===================================================================== MMA issuer (one elected thread)
         if (elect_one()) {
+            // Descriptors are kept as 64-bit values and advanced with plain adds (the 14-bit start-address field never
+            // carries: shared memory is < 256 KB): the unrolled body is two 64-bit uniform adds + one UTCHMMA per MMA.
             const uint32_t idesc = umma_idesc_tf32(128, (n_this + 15) & ~15);
-            const uint32_t a_ring_lo = desc_lo(smem_u32(a_ring)), b_ring_lo = desc_lo(smem_u32(b_ring));
+            const uint64_t a_desc0 = umma_desc(a_ring), b_desc0 = umma_desc(b_ring);
             const int RB = p.RB, nchunks = p.nchunks, a_stages = p.a_stages, b_slots = p.b_slots, npad = p.npad;
-            const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4, b_slot16 = (uint32_t)p.b_slot >> 4;
-            const uint32_t a_half16 = (uint32_t)p.a_half >> 4, b_half16 = (uint32_t)p.b_half >> 4;
+            const uint64_t a_stage16 = (uint64_t)(p.a_stage >> 4), b_slot16 = (uint64_t)(p.b_slot >> 4);
+            const uint64_t a_half16 = (uint64_t)(p.a_half >> 4), b_half16 = (uint64_t)(p.b_half >> 4);
             const int nk_last = ((p.Cin_p - (nchunks - 1) * HK) + 7) >> 3;
             int as = 0, bs = 0;
             uint32_t aphase = 0, bphase = 0;
@@ -185,43 +242,28 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(X3 ? &a_split[as] : &a_full[as], aphase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const int nk = ch == nchunks - 1 ? nk_last : 4;
-                    const uint32_t a_lo = a_ring_lo + (uint32_t)as * a_stage16;
-                    if (RES && lt == 0) {   // resident weights: this chunk's taps land once per CTA
+                    const uint64_t a_desc = a_desc0 + (uint64_t)as * a_stage16;
+                    const uint32_t acc_first = ch ? 1u : 0u;
+                    if (RES) {
+                        if (lt == 0) {   // resident weights: this chunk's taps land once per CTA
 #pragma unroll 1
-                        for (int tap = 0; tap < R * S; ++tap) mbar_wait(&b_full[ch * (R * S) + tap], 0);
-                    }
-#pragma unroll
-                    for (int tap = 0; tap < R * S; ++tap) {
-                        const int r = tap / S, sx = tap % S;              // compile-time after unrolling
-                        uint32_t b_lo;
-                        if (RES) {
-                            b_lo = b_ring_lo + (uint32_t)(ch * (R * S) + tap) * b_slot16;
-                        } else {
-                            mbar_wait(&b_full[bs], bphase);
-                            b_lo = b_ring_lo + (uint32_t)bs * b_slot16;
+                            for (int tap = 0; tap < R * S; ++tap) mbar_wait(&b_full[ch * (R * S) + tap], 0);
                         }
+                        const uint64_t bd = b_desc0 + (uint64_t)(ch * (R * S)) * b_slot16;
+                        uint64_t ad = a_desc;
+                        uint32_t d = dbase;
 #pragma unroll 1
-                        for (int rb = 0; rb < RB; ++rb) {
-                            const uint32_t al = a_lo + (uint32_t)(((8 * rb + r) * 16 + sx) * 8);  // row-shifted window
-                            const uint32_t d = dbase + (uint32_t)(rb * npad);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k < nk) {
-                                    const uint32_t acc = (tap | k) ? 1u : (ch ? 1u : 0u);
-                                    if (X3) {
-                                        umma_lh(d, al + a_half16 + 2 * k, b_lo + 2 * k, DESC_HI, idesc, acc);
-                                        umma_lh(d, al + 2 * k, b_lo + b_half16 + 2 * k, DESC_HI, idesc, 1u);
-                                        umma_lh(d, al + 2 * k, b_lo + 2 * k, DESC_HI, idesc, 1u);
-                                    } else {
-                                        umma_lh(d, al + 2 * k, b_lo + 2 * k, DESC_HI, idesc, acc);
-                                    }
-                                }
-                            }
+                        for (int rb = 0; rb < RB; ++rb, ad += 1024, d += (uint32_t)npad) {
+                            if (nk == 4) issue_taps_resident<R, S, X3, 4>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, acc_first);
+                            else if (nk == 2) issue_taps_resident<R, S, X3, 2>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, acc_first);
+                            else if (nk == 1) issue_taps_resident<R, S, X3, 1>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, acc_first);
+                            else issue_taps_resident<R, S, X3, 3>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, acc_first);
                         }
-                        if (!RES) {
-                            umma_commit(&b_empty[bs]);
-                            if (++bs == b_slots) { bs = 0; bphase ^= 1; }
-                        }
+                    } else {
+                        if (nk == 4) issue_taps_streaming<R, S, X3, 4>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, acc_first, b_full, b_empty, bs, bphase, b_slots);
+                        else if (nk == 2) issue_taps_streaming<R, S, X3, 2>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, acc_first, b_full, b_empty, bs, bphase, b_slots);
+                        else if (nk == 1) issue_taps_streaming<R, S, X3, 1>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, acc_first, b_full, b_empty, bs, bphase, b_slots);
+                        else issue_taps_streaming<R, S, X3, 3>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, acc_first, b_full, b_empty, bs, bphase, b_slots);
                     }
                     umma_commit(&a_empty[as]);
                     if (++as == a_stages) { as = 0; aphase ^= 1; }
@@ -293,18 +335,19 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 for (int g = 0; g < ngroups; ++g, ++gi) {
                     const int sb = p.nstg == 2 ? (gi & 1) : 0;
                     uint8_t* sbuf = stg + sb * p.stg_bytes;
-                    // staging buffer sb was handed to the TMA store nstg groups ago: its smem read must be complete
-                    if (leader) {
-                        if (p.nstg == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (p.nstg == 1) {
+                        // single staging buffer: the store issued one group ago must have finished reading it
+                        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        epi_bar();
                     }
+                    // (two buffers: sbuf was handed to the TMA store two groups ago, and the leader waited for that
+                    //  read to complete BEFORE the barrier of the previous group - one barrier per group suffices)
                     if (p.has_resid) mbar_wait(&r_full[sb], (p.nstg == 2 ? gi >> 1 : gi) & 1);
-                    epi_bar();
                     const int cbase = g * 32;
                     const int cn = min(32, n_this - cbase);           // multiple of 4
                     float v[32];
-                    tmem_ld16(tacc + (uint32_t)cbase, v);
-                    if (cn > 16) tmem_ld16(tacc + (uint32_t)(cbase + 16), v + 16);
+                    if (cn > 16) tmem_ld32(tacc + (uint32_t)cbase, v);
+                    else tmem_ld16(tacc + (uint32_t)cbase, v);
                     if (valid) {
                         const float4* rrow = reinterpret_cast<const float4*>(rbuf + sb * p.stg_bytes + srow * 128);
                         float4* orow = reinterpret_cast<float4*>(sbuf + srow * 128);
@@ -329,6 +372,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> TMA store reads
                     __syncwarp();
                     if (p.has_resid && lane == 0) mbar_arrive(&r_empty[sb]);       // residual buffer consumed
+                    if (leader && p.nstg == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     epi_bar();
                     if (leader) {
                         tma_store_4d(&tmY, sbuf, cout0 + cbase, w0, h0 + 8 * rb, n);

@@ -272,6 +272,7 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
     const int budget = (p.tmem_cols <= 256 && tiles * splits > sms && !p.x3) ? 100 * 1024 : 200 * 1024;
     const int a_slot = (p.na_max * BOX_BYTES) << p.x3, b_slot = (p.nb_max * BOX_BYTES) << p.x3;
     p.a_slots = p.chunks_per_split < 2 ? 1 : 2;
+    if (p.x3 && p.a_slots * a_slot + 2 * b_slot + 1536 > WSMEM_MAX) p.a_slots = 1;   // 3xTF32 slots are twice as big
     int bs = (budget - p.a_slots * a_slot) / b_slot;
     const long long b_loads = (long long)p.chunks_per_split * p.taps_per_cta;
     if (bs > MAX_B) bs = MAX_B;

@@ -319,3 +319,43 @@ def test_conv_halo_declines_small_layers_untouched():
                        0, 0, 0.0, y.data_ptr(), 64, 64, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert rc == -2 and float(y.abs().max()) == 0.0
+
+
+WGRAD_HALO_CASES = [
+    # cin, cout, k, pad, H, W, N
+    (48, 48, 3, 1, 64, 64, 4),       # two ci chunks (32 + 16), co = 48
+    (24, 24, 3, 1, 64, 64, 8),
+    (4, 32, 3, 1, 32, 32, 2),        # image input
+    (128, 32, 3, 1, 32, 32, 2),      # 4 ci chunks on the TMEM columns
+    (32, 128, 3, 1, 32, 32, 2),
+    (140, 32, 3, 1, 30, 26, 3),      # 5 chunks -> 2 chunk groups, partial tiles
+    (16, 64, 4, 0, 35, 35, 2),       # 4x4 valid: all four tap rows useful
+    (64, 128, 4, 0, 61, 61, 2),
+    (36, 12, 3, 1, 64, 64, 4),       # co = 12 -> N = 16
+    (64, 256, 3, 1, 32, 32, 2),      # two co tiles
+]
+
+
+@pytest.mark.parametrize('kernel', ['whalo', 'whalo_x3'])
+@pytest.mark.parametrize('cin,cout,k,pad,H,W,N', WGRAD_HALO_CASES)
+def test_wgrad_halo_matches_torch_autograd(cin, cout, k, pad, H, W, N, kernel):
+    """csrc/wgrad_halo.cu (halo windows, tap rows on the M dimension) vs autograd of F.conv2d in double."""
+    from monkey_net_b200 import lib
+    torch.manual_seed(cin + cout)
+    dev = torch.device('cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    x = torch.randn(N, H, W, cin, device=dev)
+    dy = torch.randn(N, Ho, Wo, cout, device=dev)
+    d = torch.full((k * k * cin * cout,), float('nan'), device=dev)
+    x3 = kernel == 'whalo_x3'
+    lib.call('mk_conv2d_wgrad_halo_x3' if x3 else 'mk_conv2d_wgrad_halo', x.data_ptr(), N, H, W, cin, cin, dy.data_ptr(),
+             cout, cout, k, k, pad, d.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert not torch.isnan(d).any()
+    wz = torch.zeros(cout, cin, k, k, device=dev, dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), wz, None, padding=pad)
+    (gw,) = torch.autograd.grad(y, wz, dy.double().permute(0, 3, 1, 2))
+    ref = gw.permute(2, 3, 1, 0).reshape(-1)          # (Co,Ci,R,S) -> [tap][Ci][Co]
+    err = float((d.double() - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+    assert err < (4e-5 if x3 else 2e-3), err

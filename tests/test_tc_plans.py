@@ -80,6 +80,37 @@ def test_every_layer_has_a_valid_tensor_core_plan(name, res, batch):
                 assert gx < 2 ** 31 and gy <= 65535 and gz <= 65535
                 if tag == 'fwd_act':
                     assert ksplit == 1                                                            # linear epilogue only
+            # 3xTF32 plans of the per-tap kernels (twice the stage bytes)
+            for tag, a in jobs[:1] + jobs[2:]:
+                a3 = list(a)
+                a3[4] |= 2
+                rc, o = plan(lib, 'mk_conv2d_tc_plan', *a3)
+                assert rc == 0 and o[3] <= 227 * 1024 and 2 <= o[4] <= 8, (name, tag, 'x3', a3, lib.mk_last_error())
+            rc, o = plan(lib, 'mk_conv2d_wgrad_tc_plan', N, H, W, cin_p, cop, k, k, pad | 256)
+            assert rc == 0 and o[3] <= 227 * 1024 and o[6] * o[7] <= 512, (name, 'wgrad x3', lib.mk_last_error())
+            # halo-window persistent kernels: either a valid plan or a clean decline (-2, few-tile / small-image layers)
+            for x3 in (0, 1):
+                for tag, (n_, h_, w_, ci_, k_, p_, co_, res_) in (
+                        ('halo fwd', (N, H, W, cin_p, k, pad, cop, 0)), ('halo fwd+res', (N, H, W, cin_p, k, pad, cop, 1)),
+                        ('halo dgrad', (N, ho, wo, cop, k, k - 1 - pad, cin_p, 0))):
+                    rc, o = plan(lib, 'mk_conv2d_tc_halo_plan', n_, h_, w_, ci_, k_, k_, p_, co_, res_, x3)
+                    assert rc in (0, -2), (name, tag, lib.mk_last_error())
+                    if rc == 0:
+                        gx, gy, rb, smem, a_st, b_sl, resident, tmem, ntiles, halo_rows, a_stage, b_slot, twv, ngr, npad, fl = o
+                        assert k_ in (1, 3, 4) and smem <= 227 * 1024 and 2 <= a_st <= 4 and rb in (1, 2, 4)
+                        assert 2 * rb * npad <= tmem <= 512 and halo_rows == 8 * rb + k_ and twv == 17 - k_
+                        assert (resident and b_sl == k_ * k_ * ((ci_ + 31) // 32) <= 40) or (not resident and 2 <= b_sl <= 8)
+                        assert gx * gy <= 148 and ntiles >= gx and (fl & 1) == x3 and (fl >> 1) in (1, 2)
+                        nstg = fl >> 1
+                        assert a_st * a_stage + b_sl * b_slot + nstg * (1 + res_) * twv * 8 * 128 + 2048 == smem
+                rc, o = plan(lib, 'mk_conv2d_wgrad_halo_plan', N, H, W, cin_p, cop, k, k, pad, x3)
+                assert rc in (0, -2), (name, 'wgrad halo', lib.mk_last_error())
+                if rc == 0:
+                    cot, cig, spl, smem, stages, tr, nci, nco, tmem, ntiles, tps, co_pad, stage, f3, twv, tilesh = o
+                    assert k in (3, 4) and smem <= 227 * 1024 and 2 <= stages <= 4 and tr in (4, 8)
+                    assert nci * k * co_pad <= tmem <= 512 and cig * nci >= (cin_p + 31) // 32 and nco * 32 >= min(cop, 128)
+                    assert tps * spl >= ntiles and tps * (spl - 1) < ntiles and spl <= 65535
+                    assert stage == ((nci * (tr + 4) + nco * tr) * 2048) << x3 and stages * stage + 2048 == smem
             rc, o = plan(lib, 'mk_conv2d_wgrad_tc_plan', N, H, W, cin_p, cop, k, k, pad)
             assert rc == 0, (name, 'wgrad', lib.mk_last_error())
             gx, gy, gz, smem, a_slots, b_slots, taps, npad, tmem, tw, th, tn, nchunks, cps, na, nb = o
