@@ -247,6 +247,16 @@ int mk_loss_bwd(int kind, const float* a, const long long* stride_a, const float
                 int B, int C, int D, int H, int W, float weight, const float* gout, float* da, float* db,
                 void* stream);
 
+/* ---- multi-GPU: one-shot all-reduce of the packed BN statistics over NVLink peer memory (csrc/p2p.cu), replacing one
+ * NCCL call per BN layer per direction (sync_batchnorm/batchnorm.py:90-125).  Every rank allocates
+ * mk_stats_allreduce_bytes() bytes of SYMMETRIC memory (zero-filled once); `peers` is a HOST array of `world` device
+ * pointers (rank r's buffer as mapped in this process); `seq` a zero-initialised device uint64 owned by the
+ * communicator.  Sums `n` doubles (is_double) or floats at `local` in place, in rank order (bit-identical on all
+ * ranks); the sequence number lives on the device, so the launch is CUDA-graph capturable. */
+int mk_stats_allreduce_bytes(void);
+int mk_stats_allreduce(void* local, int n, int is_double, const unsigned long long* peers, int rank, int world,
+                       unsigned long long* seq, void* stream);
+
 /* ---- optimiser (train.py:81-83,118-136): fused Adam over one flat fp32 span. */
 int mk_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                  float eps, float bias_c1, float bias_c2, void* stream);

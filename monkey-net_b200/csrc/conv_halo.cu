@@ -25,8 +25,8 @@
 //     staging rows in shared memory -> cp.async.bulk.tensor store of {32 ch, TWv, 8} boxes: full-line writes, image /
 //     channel edges clipped by the TMA unit.  The residual tile is prefetched by its own TMA producer warp.
 //
-// Warp roles (288 threads): 0-3 = epilogue (TMEM lane quarter = warp), 4 = TMEM allocator + residual producer,
-// 5 = TMA producer (halo + weights), 6-7 = 3xTF32 splitters, 8 = MMA issuer.  The issuer has the highest warp id of
+// Warp roles (352 threads): 0-3 = epilogue (TMEM lane quarter = warp), 4 = TMEM allocator + residual producer,
+// 5 = TMA producer (halo + weights), 6-7 and 9-10 = 3xTF32 splitters, 8 = MMA issuer.  The issuer has the highest warp id of
 // its scheduler (the arbiter is highest-wid-first) and its loop is fully unrolled over the filter taps (kernel
 // template <R, S, X3, RESIDENT>): with N = 48 an MMA retires in 24 clk, so the single issuing thread can afford only
 // a handful of instructions per MMA - the first version spent ~45 (runtime tap decode, 64-bit descriptor math, role
@@ -42,7 +42,7 @@ using namespace mk_tc;
 constexpr int HK = 32;                 // fp32 channels per chunk = 128 bytes
 constexpr int MAXA = 4, MAXB = 40;     // ring depth bounds (MAXB also bounds the resident slots: 9 taps x 4 chunks = 36)
 constexpr int H_SMEM_MAX = 227 * 1024;
-constexpr int H_THREADS = 288;
+constexpr int H_THREADS = 352;
 
 struct HP {
     int N, Ho, Wo, Cout_p, Cin_p, R, S, pad;
@@ -168,7 +168,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (p.has_resid) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     }
     if (warp == 8 && lane == 0) {
-        for (int i = 0; i < MAXA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_split[i], 2); }
+        for (int i = 0; i < MAXA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_split[i], 4); }
         for (int i = 0; i < MAXB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
@@ -288,10 +288,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
             }
         }
-    } else if (warp == 6 || warp == 7) {
-        // ===================================================================== 3xTF32 halo splitters (64 threads)
+    } else if (warp == 6 || warp == 7 || warp >= 9) {
+        // ===================================================================== 3xTF32 halo splitters (4 warps)
         if (X3) {
-            const int tid = threadIdx.x - 192;
+            const int tid = (warp >= 9 ? warp - 7 : warp - 6) * 32 + lane;      // 0..127
             const int n4 = p.a_half >> 4;
             int ai = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
@@ -300,13 +300,23 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(&a_full[as], (ai / p.a_stages) & 1);
                     float4* hi = reinterpret_cast<float4*>(a_ring + as * p.a_stage);
                     float4* lo = reinterpret_cast<float4*>(a_ring + as * p.a_stage + p.a_half);
-#pragma unroll 4
-                    for (int i = tid; i < n4; i += 64) {
-                        float4 v = hi[i], h, l;
-                        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                        split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                        hi[i] = h;
-                        lo[i] = l;
+                    // four independent 16-byte pieces per thread and pass: the in-place hi store may alias the next
+                    // load as far as the compiler knows, so a one-piece loop runs at one shared-memory round trip each
+                    for (int i0 = tid; i0 < n4; i0 += 512) {
+                        float4 v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (i0 + 128 * j < n4) v[j] = hi[i0 + 128 * j];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (i0 + 128 * j < n4) {
+                                float4 h, l;
+                                split_tf32(v[j].x, h.x, l.x); split_tf32(v[j].y, h.y, l.y);
+                                split_tf32(v[j].z, h.z, l.z); split_tf32(v[j].w, h.w, l.w);
+                                hi[i0 + 128 * j] = h;
+                                lo[i0 + 128 * j] = l;
+                            }
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -444,12 +454,15 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
         if (rb > 1 && 8 * (rb / 2) >= Ho) break;                           // the extra row-blocks would all be empty
         const int halo_rows = 8 * rb + R;                                   // (R-1) halo rows + 1 overrun row
         const int a_stage = (halo_rows * 16 * 128) << p.x3;
-        int nstg = 0, res = 0;
+        int nstg = 0, res = 0, bslots = 0;
         for (int ns = 2; ns >= 1 && !nstg; --ns) {
             const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + 2048;
-            if (nB <= MAXB && nB * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) { nstg = ns; res = 1; }
-            else if (2 * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX && ns == 1) { nstg = ns; res = 0; }
-            else if (3 * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) { nstg = ns; res = 0; }
+            if (nB <= MAXB && nB * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) { nstg = ns; res = 1; bslots = nB; }
+            else if ((ns == 1 ? 2 : 3) * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) {
+                nstg = ns; res = 0;
+                bslots = (H_SMEM_MAX - fixed - 2 * a_stage) / p.b_slot;
+                if (bslots > 8) bslots = 8;
+            }
         }
         if (!nstg) break;
         const double mma_clk = (double)rb * R * S * ksteps * (128.0 * p.b_rows / 256.0) * (p.x3 ? 3 : 1);
@@ -461,7 +474,14 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
         const double waves = (double)tiles / gx;
         const double quant = (double)((tiles + gx - 1) / gx) / (waves > 1e-9 ? waves : 1e-9);
         const double rows_eff = (double)Ho / ((Ho + 8 * rb - 1) / (8 * rb) * 8.0 * rb);
-        const double score = (mma_clk > l2 / 40.0 ? mma_clk : l2 / 40.0) / rb * quant / rows_eff;
+        // a streamed weight slot is consumed in (rb * K steps) MMAs but takes a full L2 round trip (~2800 clk) to
+        // refill: with `bslots` slots in flight the ring sustains one slot per 2800 / bslots clk
+        const double slot_clk = mma_clk / (R * S * p.nchunks);
+        const double ring_clk = res ? 0.0 : (2800.0 / bslots) * R * S * p.nchunks;
+        double t = mma_clk > l2 / 40.0 ? mma_clk : l2 / 40.0;
+        if (ring_clk > t) t = ring_clk;
+        (void)slot_clk;
+        const double score = t / rb * quant / rows_eff;
         if (!best_rb || score < best_score * 0.97) { best_rb = rb; best_score = score; best_nstg = nstg; best_res = res; }
     }
     if (!best_rb) {
@@ -495,7 +515,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
         p.b_slots = (budget - 2 * p.a_stage) / p.b_slot;
         if (p.b_slots > 8) {
             p.b_slots = 8;
-            if (budget - 8 * p.b_slot >= 3 * p.a_stage) p.a_stages = 3;
+            p.a_stages = (budget - 8 * p.b_slot) / p.a_stage;
         }
     }
     if (p.a_stages > MAXA) p.a_stages = MAXA;

@@ -25,7 +25,7 @@
 namespace {
 using namespace mk_tc;
 
-constexpr int WH_THREADS = 256;   // warps 0-3 epilogue, 4 TMEM alloc, 5 TMA producer, 6-7 zero / split helpers ... 8? no: 7 = MMA
+constexpr int WH_THREADS = 256;   // warps 0-3 helpers (zero / split) then epilogue, 4 TMEM alloc, 5 TMA producer, 7 MMA issuer
 constexpr int WH_SMEM_MAX = 227 * 1024;
 constexpr int WH_MAXST = 4;
 
@@ -101,7 +101,7 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDy) : "memory");
     }
     if (warp == 7 && lane == 0) {
-        for (int i = 0; i < WH_MAXST; ++i) { mbar_init(&full[i], 1); mbar_init(&ready[i], 2); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < WH_MAXST; ++i) { mbar_init(&full[i], 1); mbar_init(&ready[i], 4); mbar_init(&empty[i], 1); }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -136,10 +136,12 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 if (++st == p.stages) { st = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 6 || (warp == 4)) {
-        // ===================================================================== helpers (2 warps): zero the junk columns
-        // of dY (their shifted X partners wrap into the next image row) and, in 3xTF32 mode, split both operands
-        const int tid = (warp == 6 ? 0 : 32) + lane;
+    }
+    if (warp < 4 && t1 > t0) {
+        // ===================================================================== helpers = the four epilogue warps, idle
+        // until the last tile: zero the junk columns of dY (their shifted X partners wrap into the next image row) and,
+        // in 3xTF32 mode, split both operands hi / lo in place
+        const int tid = threadIdx.x;   // 0..127
         int st = 0;
         uint32_t ph = 0;
         for (int tile = t0; tile < t1; ++tile) {
@@ -150,30 +152,47 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 float4* hi = reinterpret_cast<float4*>(sb);
                 float4* lo = reinterpret_cast<float4*>(sb + p.x_region);
                 const int n4 = (nci * p.xa_half) >> 4;
-                for (int i = tid; i < n4; i += 64) {
-                    float4 v = hi[i], h, l;
-                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                    hi[i] = h;
-                    lo[i] = l;
+                for (int i0 = tid; i0 < n4; i0 += 512) {
+                    float4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i0 + 128 * j < n4) v[j] = hi[i0 + 128 * j];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i0 + 128 * j < n4) {
+                            float4 h, l;
+                            split_tf32(v[j].x, h.x, l.x); split_tf32(v[j].y, h.y, l.y);
+                            split_tf32(v[j].z, h.z, l.z); split_tf32(v[j].w, h.w, l.w);
+                            hi[i0 + 128 * j] = h;
+                            lo[i0 + 128 * j] = l;
+                        }
                 }
                 float4* dhi = reinterpret_cast<float4*>(dyb);
                 float4* dlo = reinterpret_cast<float4*>(dyb + p.dy_region);
                 const int m4 = (nco * p.dy_half) >> 4;
-                for (int i = tid; i < m4; i += 64) {
-                    const int pix = (i >> 3) & (TR * 16 - 1);           // 8 float4 per 128-byte pixel row
-                    float4 v = dhi[i], h, l;
-                    if ((pix & 15) >= p.TWv) v = f4zero();
-                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                    dhi[i] = h;
-                    dlo[i] = l;
+                for (int i0 = tid; i0 < m4; i0 += 512) {
+                    float4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i0 + 128 * j < m4) v[j] = dhi[i0 + 128 * j];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i0 + 128 * j < m4) {
+                            const int i = i0 + 128 * j;
+                            const int pix = (i >> 3) & (TR * 16 - 1);       // 8 float4 per 128-byte pixel row
+                            if ((pix & 15) >= p.TWv) v[j] = f4zero();
+                            float4 h, l;
+                            split_tf32(v[j].x, h.x, l.x); split_tf32(v[j].y, h.y, l.y);
+                            split_tf32(v[j].z, h.z, l.z); split_tf32(v[j].w, h.w, l.w);
+                            dhi[i] = h;
+                            dlo[i] = l;
+                        }
                 }
             } else {
                 // junk pixel rows only: (16 - TWv) of every 16 rows, 8 float4 each
                 const int junk = 16 - p.TWv;
                 const int per_box = TR * junk * 8;
-                for (int i = tid; i < nco * per_box; i += 64) {
+                for (int i = tid; i < nco * per_box; i += 128) {
                     const int box = i / per_box, rem = i - box * per_box;
                     const int prow = rem >> 3, q4 = rem & 7;
                     const int row = prow / junk, col = p.TWv + (prow - row * junk);
@@ -185,7 +204,8 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             if (lane == 0) mbar_arrive(&ready[st]);
             if (++st == p.stages) { st = 0; ph ^= 1; }
         }
-    } else if (warp == 7) {
+    }
+    if (warp == 7) {
         // ===================================================================== MMA issuer
         if (elect_one() && t1 > t0) {
             // M = 128 = 4 tap rows x 32 channels (a_major = b_major = MN), N = co_pad

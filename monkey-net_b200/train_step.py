@@ -86,17 +86,43 @@ def train_iteration(generator_full_par, discriminator_full_par, optimizers, trai
     return g_vals, loss_values
 
 
+_COMM_STREAM = {}
+
+
+def _comm_stream(device):
+    if device not in _COMM_STREAM:
+        _COMM_STREAM[device] = torch.cuda.Stream(device=device)
+    return _COMM_STREAM[device]
+
+
 def _train_iteration_flat(generator_full_par, discriminator_full_par, optimizers, train_params, x):
-    """train.py:110-136 with FlatAdam: `step()` = all-reduce (N > 1) + update + zero_grad of that group in one launch."""
+    """train.py:110-136 with FlatAdam: `step()` = all-reduce (N > 1) + update + zero_grad of that group in one launch.
+
+    Data parallel (N > 1): the discriminator step reads the generated frames and keypoints DETACHED
+    (train.py:71, detach_kp_discriminator) - it depends on neither the generator's nor the keypoint detector's UPDATED
+    parameters.  Their flat gradient all-reduces (NVLink, ~170 MB at taichi) and Adam launches therefore run on a side
+    stream concurrently with the whole discriminator step and are joined at the end of the iteration - the collective
+    is off the critical path (fork / join is captured in the CUDA graph as stream dependencies)."""
+    from . import dist as mkdist
     opt_g, opt_d, opt_kp = optimizers
     out = generator_full_par(x)
     loss_values = [val.mean() for val in out[:-2]]
     generated, kp_joined = out[-2], out[-1]
     loss = sum(loss_values)
     loss.backward(retain_graph=not train_params['detach_kp_discriminator'])
-    opt_g.sync_gradients(); opt_g.step()      # optimizer_generator.step(); .zero_grad()
+    overlap = mkdist.world() > 1 and train_params['detach_kp_discriminator'] and loss.is_cuda
+    side = None
+    if overlap:
+        main = torch.cuda.current_stream()
+        side = _comm_stream(loss.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            opt_g.sync_gradients(); opt_g.step()
+            opt_kp.sync_gradients(); opt_kp.step()
+    else:
+        opt_g.sync_gradients(); opt_g.step()      # optimizer_generator.step(); .zero_grad()
     opt_d.zero_grad()                         # optimizer_discriminator.zero_grad()
-    if train_params['detach_kp_discriminator']:
+    if train_params['detach_kp_discriminator'] and not overlap:
         opt_kp.sync_gradients(); opt_kp.step()
     g_vals = loss_values
     loss_values = [val.mean() for val in discriminator_full_par(x, kp_joined, generated)]
@@ -105,6 +131,8 @@ def _train_iteration_flat(generator_full_par, discriminator_full_par, optimizers
     opt_d.sync_gradients(); opt_d.step()
     if not train_params['detach_kp_discriminator']:
         opt_kp.sync_gradients(); opt_kp.step()
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)   # join: the next iteration reads the updated G / KP parameters
     return g_vals, loss_values
 
 

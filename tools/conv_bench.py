@@ -17,16 +17,21 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch  # noqa: E402
 import yaml  # noqa: E402
 
-CONV = ('mk_conv2d', 'mk_conv2d_wgrad', 'mk_conv2d_tc', 'mk_conv2d_wgrad_tc')
+CONV = ('mk_conv2d', 'mk_conv2d_wgrad', 'mk_conv2d_tc', 'mk_conv2d_wgrad_tc', 'mk_conv2d_tc_x3', 'mk_conv2d_wgrad_tc_x3',
+        'mk_conv2d_tc_halo', 'mk_conv2d_tc_halo_x3', 'mk_conv2d_wgrad_halo', 'mk_conv2d_wgrad_halo_x3')
 
 
 def signature(name, a):
-    if name in ('mk_conv2d_tc', 'mk_conv2d'):
+    if name in ('mk_conv2d_tc_halo', 'mk_conv2d_tc_halo_x3'):
+        N, H, W, Ci, R, pad, Co = a[1], a[2], a[3], a[4], a[7], a[9], a[17]
+        Ho, Wo = H + 2 * pad - R + 1, W + 2 * pad - R + 1
+        return 'N%d %dx%d ci%d co%d k%d p%d' % (N, H, W, Ci, Co, R, pad), 2.0 * N * Ho * Wo * Ci * Co * R * R
+    if name in ('mk_conv2d_tc', 'mk_conv2d', 'mk_conv2d_tc_x3'):
         N, H, W, Ci, ups, R, pad, Co = a[1], a[2], a[3], a[4], a[6], a[8], a[10], a[18]
         Ho, Wo = (H << ups) + 2 * pad - R + 1, (W << ups) + 2 * pad - R + 1
         fl = 2.0 * N * Ho * Wo * Ci * Co * R * R
         return 'N%d %dx%d ci%d co%d k%d p%d%s' % (N, H, W, Ci, Co, R, pad, ' ups' if ups else ''), fl
-    if name == 'mk_conv2d_wgrad_tc':
+    if name in ('mk_conv2d_wgrad_tc', 'mk_conv2d_wgrad_tc_x3', 'mk_conv2d_wgrad_halo', 'mk_conv2d_wgrad_halo_x3'):
         N, H, W, Ci, Co, R, pad = a[1], a[2], a[3], a[4], a[7], a[9], a[11]
     else:
         N, H, W, Ci, ups, Co, R, pad = a[1], a[2], a[3], a[4], a[6], a[8], a[10], a[12]

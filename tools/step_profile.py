@@ -21,13 +21,15 @@ import torch  # noqa: E402
 import yaml  # noqa: E402
 
 KERNEL_OF = {'mk_conv2d_tc': 'k_conv_tc', 'mk_conv2d_wgrad_tc': 'k_wgrad_tc', 'mk_conv2d': 'k_conv_ffma',
-             'mk_conv2d_wgrad': 'k_conv_wgrad'}
+             'mk_conv2d_wgrad': 'k_conv_wgrad', 'mk_conv2d_tc_x3': 'k_conv_tc', 'mk_conv2d_wgrad_tc_x3': 'k_wgrad_tc',
+             'mk_conv2d_tc_halo': 'k_conv_halo', 'mk_conv2d_tc_halo_x3': 'k_conv_halo',
+             'mk_conv2d_wgrad_halo': 'k_wgrad_halo', 'mk_conv2d_wgrad_halo_x3': 'k_wgrad_halo'}
 
 
 def short(name):
     name = name.replace('(anonymous namespace)::', '').replace('void ', '')
     name = re.sub(r'\(.*', '', name)
-    return re.sub(r'<.*', '', name) if name.startswith('at::') else name
+    return re.sub(r'<.*', '', name) if (name.startswith('at::') or name.startswith('k_conv_halo') or name.startswith('k_wgrad_halo')) else name
 
 
 def main():
@@ -54,17 +56,21 @@ def main():
          'video': torch.rand(args.batch, 3, 1, args.res, args.res, device=dev)}
     # record the conv call sequence while the graph is captured (same order as the kernels in the graph)
     calls = []
-    orig = lib.call
+    orig, orig_soft = lib.call, lib.call_soft
 
     def traced(name, *a):
         if name in KERNEL_OF:
             calls.append((name, conv_bench.signature(name, a)))
         orig(name, *a)
-    lib.call = traced
-    ops.lib.call = traced
+
+    def traced_soft(name, soft, *a):
+        rc = orig_soft(name, soft, *a)
+        if rc == 0 and name in KERNEL_OF:
+            calls.append((name, conv_bench.signature(name, a)))
+        return rc
+    lib.call, lib.call_soft = traced, traced_soft
     tr.step(x)  # warm-up iterations + capture; `calls` keeps growing, the capture is the LAST iteration
-    lib.call = orig
-    ops.lib.call = orig
+    lib.call, lib.call_soft = orig, orig_soft
     per_iter = len(calls) // (tr.warmup + 1)
     calls = calls[-per_iter:]
     for _ in range(3):
