@@ -49,7 +49,7 @@ struct HP {
     int TWv, RB, tilesW, tilesH, ntiles;
     int halo_rows, a_half, a_stage, a_stages;
     int b_rows, b_half, b_slot, b_slots, resident;
-    int nchunks, ngroups, npad, tmem_cols;
+    int nchunks, ngroups, npad, acc_cols, tmem_cols;   // acc_cols = TMEM columns per accumulator (2 * npad in 3xTF32)
     int x3, lo_tap_offset;
     int stg_bytes, nstg;   // nstg = 1 or 2 staging buffers (and as many residual buffers)
     const float* scale; const float* shift; int has_resid, act; float slope;
@@ -82,7 +82,7 @@ constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 
 template <int R, int S, bool X3, int NK>
 __device__ __forceinline__ void issue_taps_resident(uint32_t d, uint64_t ad, uint64_t bd, uint64_t a_half16,
                                                     uint64_t b_half16, uint64_t b_slot16, uint32_t idesc,
-                                                    uint32_t acc_first) {
+                                                    uint32_t idesc2, uint32_t acc_first) {
 #pragma unroll
     for (int tap = 0; tap < R * S; ++tap) {
         const uint64_t a = ad + (uint64_t)(((tap / S) * 16 + (tap % S)) * 8);   // row-shifted window, 16-byte units
@@ -91,9 +91,11 @@ __device__ __forceinline__ void issue_taps_resident(uint32_t d, uint64_t ad, uin
         for (int k = 0; k < NK; ++k) {
             const uint32_t acc = (tap | k) ? 1u : acc_first;
             if (X3) {
-                umma_tf32(d, a + a_half16 + 2 * k, b + 2 * k, idesc, acc);
-                umma_tf32(d, a + 2 * k, b + b_half16 + 2 * k, idesc, 1u);
-                umma_tf32(d, a + 2 * k, b + 2 * k, idesc, 1u);
+                // A_hi x [B_hi ; B_lo] in ONE MMA of N = 2 * b_rows (the lo rows follow the hi rows in the slot): columns
+                // [0, n) collect hi*hi, [n, 2n) hi*lo - A_hi is read from shared memory once instead of twice; then
+                // A_lo x B_hi into [0, n).  The epilogue adds the two column halves.
+                umma_tf32(d, a + 2 * k, b + 2 * k, idesc2, acc);
+                umma_tf32(d, a + a_half16 + 2 * k, b + 2 * k, idesc, 1u);
             } else {
                 umma_tf32(d, a + 2 * k, b + 2 * k, idesc, acc);
             }
@@ -105,8 +107,9 @@ __device__ __forceinline__ void issue_taps_resident(uint32_t d, uint64_t ad, uin
 template <int R, int S, bool X3, int NK>
 __device__ __forceinline__ void issue_taps_streaming(uint32_t dbase, int RB, int npad, uint64_t a_desc, uint64_t b_desc0,
                                                      uint64_t a_half16, uint64_t b_half16, uint64_t b_slot16,
-                                                     uint32_t idesc, uint32_t acc_first, uint64_t* b_full,
-                                                     uint64_t* b_empty, int& bs, uint32_t& bphase, int b_slots) {
+                                                     uint32_t idesc, uint32_t idesc2, uint32_t acc_first,
+                                                     uint64_t* b_full, uint64_t* b_empty, int& bs, uint32_t& bphase,
+                                                     int b_slots) {
 #pragma unroll
     for (int tap = 0; tap < R * S; ++tap) {
         mbar_wait(&b_full[bs], bphase);
@@ -119,9 +122,8 @@ __device__ __forceinline__ void issue_taps_streaming(uint32_t dbase, int RB, int
             for (int k = 0; k < NK; ++k) {
                 const uint32_t acc = (tap | k) ? 1u : acc_first;
                 if (X3) {
-                    umma_tf32(d, a + a_half16 + 2 * k, b + 2 * k, idesc, acc);
-                    umma_tf32(d, a + 2 * k, b + b_half16 + 2 * k, idesc, 1u);
-                    umma_tf32(d, a + 2 * k, b + 2 * k, idesc, 1u);
+                    umma_tf32(d, a + 2 * k, b + 2 * k, idesc2, acc);           // A_hi x [B_hi ; B_lo], N = 2 * b_rows
+                    umma_tf32(d, a + a_half16 + 2 * k, b + 2 * k, idesc, 1u);  // A_lo x B_hi
                 } else {
                     umma_tf32(d, a + 2 * k, b + 2 * k, idesc, acc);
                 }
@@ -223,9 +225,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
             // Descriptors are kept as 64-bit values and advanced with plain adds (the 14-bit start-address field never
             // carries: shared memory is < 256 KB): the unrolled body is two 64-bit uniform adds + one UTCHMMA per MMA.
-            const uint32_t idesc = umma_idesc_tf32(128, (n_this + 15) & ~15);
+            const uint32_t idesc = umma_idesc_tf32(128, X3 ? p.b_rows : ((n_this + 15) & ~15));
+            const uint32_t idesc2 = umma_idesc_tf32(128, 2 * p.b_rows);   // 3xTF32: [B_hi ; B_lo] as one N = 2 * b_rows operand
             const uint64_t a_desc0 = umma_desc(a_ring), b_desc0 = umma_desc(b_ring);
-            const int RB = p.RB, nchunks = p.nchunks, a_stages = p.a_stages, b_slots = p.b_slots, npad = p.npad;
+            const int RB = p.RB, nchunks = p.nchunks, a_stages = p.a_stages, b_slots = p.b_slots, npad = p.acc_cols;
             const uint64_t a_stage16 = (uint64_t)(p.a_stage >> 4), b_slot16 = (uint64_t)(p.b_slot >> 4);
             const uint64_t a_half16 = (uint64_t)(p.a_half >> 4), b_half16 = (uint64_t)(p.b_half >> 4);
             const int nk_last = ((p.Cin_p - (nchunks - 1) * HK) + 7) >> 3;
@@ -254,16 +257,16 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         uint32_t d = dbase;
 #pragma unroll 1
                         for (int rb = 0; rb < RB; ++rb, ad += 1024, d += (uint32_t)npad) {
-                            if (nk == 4) issue_taps_resident<R, S, X3, 4>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, acc_first);
-                            else if (nk == 2) issue_taps_resident<R, S, X3, 2>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, acc_first);
-                            else if (nk == 1) issue_taps_resident<R, S, X3, 1>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, acc_first);
-                            else issue_taps_resident<R, S, X3, 3>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, acc_first);
+                            if (nk == 4) issue_taps_resident<R, S, X3, 4>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first);
+                            else if (nk == 2) issue_taps_resident<R, S, X3, 2>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first);
+                            else if (nk == 1) issue_taps_resident<R, S, X3, 1>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first);
+                            else issue_taps_resident<R, S, X3, 3>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first);
                         }
                     } else {
-                        if (nk == 4) issue_taps_streaming<R, S, X3, 4>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, acc_first, b_full, b_empty, bs, bphase, b_slots);
-                        else if (nk == 2) issue_taps_streaming<R, S, X3, 2>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, acc_first, b_full, b_empty, bs, bphase, b_slots);
-                        else if (nk == 1) issue_taps_streaming<R, S, X3, 1>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, acc_first, b_full, b_empty, bs, bphase, b_slots);
-                        else issue_taps_streaming<R, S, X3, 3>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, acc_first, b_full, b_empty, bs, bphase, b_slots);
+                        if (nk == 4) issue_taps_streaming<R, S, X3, 4>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first, b_full, b_empty, bs, bphase, b_slots);
+                        else if (nk == 2) issue_taps_streaming<R, S, X3, 2>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first, b_full, b_empty, bs, bphase, b_slots);
+                        else if (nk == 1) issue_taps_streaming<R, S, X3, 1>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first, b_full, b_empty, bs, bphase, b_slots);
+                        else issue_taps_streaming<R, S, X3, 3>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first, b_full, b_empty, bs, bphase, b_slots);
                     }
                     umma_commit(&a_empty[as]);
                     if (++as == a_stages) { as = 0; aphase ^= 1; }
@@ -341,7 +344,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int rb = 0; rb < p.RB; ++rb) {
-                const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.RB + rb) * p.npad);
+                const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.RB + rb) * p.acc_cols);
                 for (int g = 0; g < ngroups; ++g, ++gi) {
                     const int sb = p.nstg == 2 ? (gi & 1) : 0;
                     uint8_t* sbuf = stg + sb * p.stg_bytes;
@@ -358,6 +361,13 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     float v[32];
                     if (cn > 16) tmem_ld32(tacc + (uint32_t)cbase, v);
                     else tmem_ld16(tacc + (uint32_t)cbase, v);
+                    if (X3) {   // hi*lo partial products live in the second column half of the accumulator
+                        float u[32];
+                        if (cn > 16) tmem_ld32(tacc + (uint32_t)(p.npad + cbase), u);
+                        else tmem_ld16(tacc + (uint32_t)(p.npad + cbase), u);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += u[j];
+                    }
                     if (valid) {
                         const float4* rrow = reinterpret_cast<const float4*>(rbuf + sb * p.stg_bytes + srow * 128);
                         float4* orow = reinterpret_cast<float4*>(sbuf + srow * 128);
@@ -450,7 +460,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     double best_score = 0.0;
     int best_rb = 0, best_nstg = 0, best_res = 0;
     for (int rb = 1; rb <= 4; rb <<= 1) {
-        if (2 * rb * p.npad > 512) break;                                  // double-buffered accumulators in TMEM
+        if (2 * rb * (p.npad << p.x3) > 512) break;                        // double-buffered accumulators in TMEM
         if (rb > 1 && 8 * (rb / 2) >= Ho) break;                           // the extra row-blocks would all be empty
         const int halo_rows = 8 * rb + R;                                   // (R-1) halo rows + 1 overrun row
         const int a_stage = (halo_rows * 16 * 128) << p.x3;
@@ -520,7 +530,8 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     }
     if (p.a_stages > MAXA) p.a_stages = MAXA;
     MK_REQUIRE(p.a_stages >= 2 && (p.resident || p.b_slots >= 2), "mk_conv2d_tc_halo: ring plan failed");
-    const int cols = 2 * p.RB * p.npad;
+    p.acc_cols = p.npad << p.x3;
+    const int cols = 2 * p.RB * p.acc_cols;
     p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
     const int smem_bytes = p.a_stages * p.a_stage + p.b_slots * p.b_slot + fixed;
     MK_REQUIRE(smem_bytes <= H_SMEM_MAX, "mk_conv2d_tc_halo: shared memory plan exceeds 227 KB (%d)", smem_bytes);
