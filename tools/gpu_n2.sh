@@ -1,5 +1,8 @@
 #!/bin/bash
-# 2-GPU visit (charged x2: keep it short, every command under its own tight timeout)
+# 2-GPU visit: on-GPU N-rank == 1-rank invariant, weak scaling of the headline step with and without the peer-memory BN statistics
 mkdir -p gpurun_out
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "rc=$?" >> gpurun_out/bench_n2.err
-cut -c1-200 gpurun_out/bench_n2.json; tail -3 gpurun_out/bench_n2.err | cut -c1-300
+nvidia-smi --query-gpu=index,name --format=csv,noheader
+timeout 280 python -m pytest tests/test_gpu_7_dist.py -q -s --tb=short -p no:cacheprovider 2>&1 | tail -12 > gpurun_out/tests_dist.log; tail -8 gpurun_out/tests_dist.log
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "n2 rc=$?"; tail -3 gpurun_out/bench_n2.err; cut -c1-400 gpurun_out/bench_n2.json
+MONKEY_B200_BN_P2P=0 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29501 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2_nccl.json 2> gpurun_out/bench_n2_nccl.err; echo "n2 nccl rc=$?"; cut -c1-300 gpurun_out/bench_n2_nccl.json
+timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-extras --no-cpu-baseline --no-kernel-bench > gpurun_out/bench_n1_same_box.json 2> gpurun_out/bench_n1_same_box.err; cut -c1-300 gpurun_out/bench_n1_same_box.json
