@@ -363,6 +363,9 @@ def run_ours(args):
     }
     if dist_check is not None:
         out['dist_check'] = dist_check
+        from monkey_net_b200 import dist as mkdist
+        out['config']['bn_statistics'] = mkdist.stats_backend() + ' (one sum per BN layer per direction; NCCL flat ' \
+            'gradient all-reduce per optimiser step, G / KP overlapped with the discriminator step)'
     if h.world == 1:
         if not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(args, cfg)

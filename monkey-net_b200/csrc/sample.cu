@@ -6,6 +6,7 @@
 // one output pixel, so the 4 taps are 128-bit loads that coalesce across the lanes of a pixel, and the output is a
 // coalesced 128-bit store.  Algorithmic bytes per call: 4*(B*C*h*w + 2*B*d*h*w + B*d*C*h*w).
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/monkey_b200.h"
 
 struct Tap {
@@ -137,10 +138,20 @@ __device__ __forceinline__ WarpTap bcast_tap(const WarpTap& t, int src) {
 // destination registers and without any scoreboard dependency on the blend of the previous pass.  (Left to itself
 // ptxas issued tap 0, consumed it, recycled its registers for the addresses of taps 2-3 and so serialised two DRAM
 // round trips per pass: ncu long-scoreboard 9.4 stall cycles per issue at 33 % DRAM.)
+// CA = cache the line in L1 as well (cp.async.ca): horizontally adjacent output pixels share two of their four taps, and
+// with .cg every tap went to the L2 - ncu (profiles/r1_ncu_grid_sample_fwd_v3.md) counts 272.6 MB crossing L2->SM for
+// a 67 MB input at 0 % L1 hit rate, i.e. ~9.7 TB/s of the ~12 TB/s the crossbar delivers: the kernel was bound by
+// L2->SM bandwidth, not by HBM.
+template <bool CA>
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc)
-                 : "memory");
+    if (CA)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                     "l"(gsrc)
+                     : "memory");
+    else
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                     "l"(gsrc)
+                     : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(256) k_grid_sample_fwd(const float* __restrict
 // cp.async, GS_STAGES passes in flight per warp.  V = 1 serves every level up to 128 channels (measured: V = 2 on
 // the 64-channel level was not faster, 32.8 vs 31.1 us, its larger staging buffer costs a resident CTA); V = 2 covers
 // the 132..256-channel levels.
-template <int V, int GS_STAGES>
+template <int V, int GS_STAGES, bool CA>
 __global__ void __launch_bounds__(256) k_grid_sample_fwd_async(const float* __restrict__ inp, int h, int w, int cv,
                                                                int ld, const float* __restrict__ deform, int d, int h0,
                                                                int w0, int mode, float* __restrict__ out, int ldo,
@@ -264,10 +275,10 @@ __global__ void __launch_bounds__(256) k_grid_sample_fwd_async(const float* __re
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     if (v < nv) {
-                        cp_async16(b + (4 * v + 0) * 32, p0);
-                        cp_async16(b + (4 * v + 1) * 32, p0 + dxb);
-                        cp_async16(b + (4 * v + 2) * 32, p0 + dyb);
-                        cp_async16(b + (4 * v + 3) * 32, p0 + dyb + dxb);
+                        cp_async16<CA>(b + (4 * v + 0) * 32, p0);
+                        cp_async16<CA>(b + (4 * v + 1) * 32, p0 + dxb);
+                        cp_async16<CA>(b + (4 * v + 2) * 32, p0 + dyb);
+                        cp_async16<CA>(b + (4 * v + 3) * 32, p0 + dyb + dxb);
                     }
                     p0 += vstep;
                 }
@@ -302,13 +313,13 @@ __global__ void __launch_bounds__(256) k_grid_sample_fwd_async(const float* __re
     }
 }
 
-template <int V, int GS_STAGES>
+template <int V, int GS_STAGES, bool CA>
 static int launch_gs_async(const float* inp, int B, int h, int w, int Cp, int ld, const float* deform, int d, int h0,
                            int w0, int mode, float* out, int ldo, cudaStream_t st) {
     const int smem = 8 * GS_STAGES * 4 * V * 32 * (int)sizeof(float4);
     static unsigned long long attr_done = 0;
     if (const unsigned long long attr_bit = mk_attr_needed(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(k_grid_sample_fwd_async<V, GS_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(k_grid_sample_fwd_async<V, GS_STAGES, CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { mk_set_error("mk_grid_sample_fwd: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done |= attr_bit;
     }
@@ -317,7 +328,7 @@ static int launch_gs_async(const float* inp, int B, int h, int w, int Cp, int ld
     const Patch pt = make_patch(h, w, Cp / 4, (long long)B * d, V, resident);
     const long long blocks = (long long)B * d * pt.tiles_x * pt.tiles_y;
     MK_REQUIRE(blocks < (1LL << 31), "mk_grid_sample_fwd: extent too large");
-    k_grid_sample_fwd_async<V, GS_STAGES><<<(unsigned)blocks, 256, smem, st>>>(inp, h, w, Cp / 4, ld, deform, d, h0, w0, mode, out,
+    k_grid_sample_fwd_async<V, GS_STAGES, CA><<<(unsigned)blocks, 256, smem, st>>>(inp, h, w, Cp / 4, ld, deform, d, h0, w0, mode, out,
                                                                     ldo, pt, make_fastdiv(pt.tiles_x),
                                                                     make_fastdiv(pt.tiles_y));
     return mk_check_launch("mk_grid_sample_fwd");
@@ -331,8 +342,17 @@ MK_EXPORT int mk_grid_sample_fwd(const float* inp, int B, int h, int w, int Cp, 
     MK_REQUIRE((long long)h * w * ld < (1LL << 31) && (long long)h * w * ldo < (1LL << 29),
                "mk_grid_sample_fwd: extent too large");
     const int cv = Cp / 4;
-    if (cv <= 32) return launch_gs_async<1, 3>(inp, B, h, w, Cp, ld, deform, d, h0, w0, mode, out, ldo, (cudaStream_t)stream);
-    if (cv <= 64) return launch_gs_async<2, 2>(inp, B, h, w, Cp, ld, deform, d, h0, w0, mode, out, ldo, (cudaStream_t)stream);
+    static int use_ca = -1;
+    if (use_ca < 0) {
+        const char* e = getenv("MONKEY_B200_GS_CA");
+        use_ca = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (cv <= 32)
+        return use_ca ? launch_gs_async<1, 3, true>(inp, B, h, w, Cp, ld, deform, d, h0, w0, mode, out, ldo, (cudaStream_t)stream)
+                      : launch_gs_async<1, 3, false>(inp, B, h, w, Cp, ld, deform, d, h0, w0, mode, out, ldo, (cudaStream_t)stream);
+    if (cv <= 64)
+        return use_ca ? launch_gs_async<2, 2, true>(inp, B, h, w, Cp, ld, deform, d, h0, w0, mode, out, ldo, (cudaStream_t)stream)
+                      : launch_gs_async<2, 2, false>(inp, B, h, w, Cp, ld, deform, d, h0, w0, mode, out, ldo, (cudaStream_t)stream);
     const Patch pt = make_patch(h, w, cv, (long long)B * d);
     const long long blocks = (long long)B * d * pt.tiles_x * pt.tiles_y;
     MK_REQUIRE(blocks < (1LL << 31), "mk_grid_sample_fwd: extent too large");
