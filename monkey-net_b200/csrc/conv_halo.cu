@@ -35,6 +35,7 @@
 #include "common.cuh"
 #include "../../include/monkey_b200.h"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 using namespace mk_tc;
@@ -79,25 +80,29 @@ constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 
 
 // One chunk's MMAs for one row-block with RESIDENT weights, fully unrolled over taps and K steps (NK compile-time):
 // per MMA two 64-bit uniform adds + one UTCHMMA, no predicates, no loop-carried vector registers.
-template <int R, int S, bool X3, int NK>
-__device__ __forceinline__ void issue_taps_resident(uint32_t d, uint64_t ad, uint64_t bd, uint64_t a_half16,
+template <int R, int S, bool X3, int NK, int RBT>
+__device__ __forceinline__ void issue_taps_resident(uint32_t d, int acc_cols, uint64_t ad, uint64_t bd, uint64_t a_half16,
                                                     uint64_t b_half16, uint64_t b_slot16, uint32_t idesc,
                                                     uint32_t idesc2, uint32_t acc_first) {
+    // tap -> K step -> row-block: consecutive MMAs alternate between the RBT independent accumulators (back-to-back
+    // MMAs into the same TMEM tile are dependent and pay a fixed ~50 clk each on top of their N/2 clk of math)
 #pragma unroll
     for (int tap = 0; tap < R * S; ++tap) {
-        const uint64_t a = ad + (uint64_t)(((tap / S) * 16 + (tap % S)) * 8);   // row-shifted window, 16-byte units
+        const uint64_t a0 = ad + (uint64_t)(((tap / S) * 16 + (tap % S)) * 8);   // row-shifted window, 16-byte units
         const uint64_t b = bd + (uint64_t)tap * b_slot16;
 #pragma unroll
         for (int k = 0; k < NK; ++k) {
             const uint32_t acc = (tap | k) ? 1u : acc_first;
-            if (X3) {
-                // A_hi x [B_hi ; B_lo] in ONE MMA of N = 2 * b_rows (the lo rows follow the hi rows in the slot): columns
-                // [0, n) collect hi*hi, [n, 2n) hi*lo - A_hi is read from shared memory once instead of twice; then
-                // A_lo x B_hi into [0, n).  The epilogue adds the two column halves.
-                umma_tf32(d, a + 2 * k, b + 2 * k, idesc2, acc);
-                umma_tf32(d, a + a_half16 + 2 * k, b + 2 * k, idesc, 1u);
-            } else {
-                umma_tf32(d, a + 2 * k, b + 2 * k, idesc, acc);
+#pragma unroll
+            for (int rb = 0; rb < RBT; ++rb) {
+                const uint64_t a = a0 + (uint64_t)(rb * 1024);               // next row-block: + 8 image rows = 16 KB
+                const uint32_t dd = d + (uint32_t)(rb * acc_cols);
+                if (X3) {
+                    umma_tf32(dd, a + 2 * k, b + 2 * k, idesc2, acc);           // A_hi x [B_hi ; B_lo], N = 2 * b_rows
+                    umma_tf32(dd, a + a_half16 + 2 * k, b + 2 * k, idesc, 1u);  // A_lo x B_hi
+                } else {
+                    umma_tf32(dd, a + 2 * k, b + 2 * k, idesc, acc);
+                }
             }
         }
     }
@@ -114,13 +119,14 @@ __device__ __forceinline__ void issue_taps_streaming(uint32_t dbase, int RB, int
     for (int tap = 0; tap < R * S; ++tap) {
         mbar_wait(&b_full[bs], bphase);
         const uint64_t b = b_desc0 + (uint64_t)bs * b_slot16;
-        uint64_t a = a_desc + (uint64_t)(((tap / S) * 16 + (tap % S)) * 8);
-        uint32_t d = dbase;
-#pragma unroll 1
-        for (int rb = 0; rb < RB; ++rb, a += 1024, d += (uint32_t)npad) {   // next row-block: + 8 image rows = 16 KB
+        const uint64_t a0 = a_desc + (uint64_t)(((tap / S) * 16 + (tap % S)) * 8);
 #pragma unroll
-            for (int k = 0; k < NK; ++k) {
-                const uint32_t acc = (tap | k) ? 1u : acc_first;
+        for (int k = 0; k < NK; ++k) {
+            const uint32_t acc = (tap | k) ? 1u : acc_first;
+            uint64_t a = a0;
+            uint32_t d = dbase;
+#pragma unroll 1
+            for (int rb = 0; rb < RB; ++rb, a += 1024, d += (uint32_t)npad) {   // alternate the independent accumulators
                 if (X3) {
                     umma_tf32(d, a + 2 * k, b + 2 * k, idesc2, acc);           // A_hi x [B_hi ; B_lo], N = 2 * b_rows
                     umma_tf32(d, a + a_half16 + 2 * k, b + 2 * k, idesc, 1u);  // A_lo x B_hi
@@ -253,15 +259,17 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             for (int tap = 0; tap < R * S; ++tap) mbar_wait(&b_full[ch * (R * S) + tap], 0);
                         }
                         const uint64_t bd = b_desc0 + (uint64_t)(ch * (R * S)) * b_slot16;
-                        uint64_t ad = a_desc;
-                        uint32_t d = dbase;
-#pragma unroll 1
-                        for (int rb = 0; rb < RB; ++rb, ad += 1024, d += (uint32_t)npad) {
-                            if (nk == 4) issue_taps_resident<R, S, X3, 4>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first);
-                            else if (nk == 2) issue_taps_resident<R, S, X3, 2>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first);
-                            else if (nk == 1) issue_taps_resident<R, S, X3, 1>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first);
-                            else issue_taps_resident<R, S, X3, 3>(d, ad, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first);
-                        }
+#define HALO_ISSUE_RES(NKK)                                                                                               \
+    do {                                                                                                                  \
+        if (RB == 1) issue_taps_resident<R, S, X3, NKK, 1>(dbase, npad, a_desc, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first); \
+        else if (RB == 2) issue_taps_resident<R, S, X3, NKK, 2>(dbase, npad, a_desc, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first); \
+        else issue_taps_resident<R, S, X3, NKK, 4>(dbase, npad, a_desc, bd, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first); \
+    } while (0)
+                        if (nk == 4) HALO_ISSUE_RES(4);
+                        else if (nk == 2) HALO_ISSUE_RES(2);
+                        else if (nk == 1) HALO_ISSUE_RES(1);
+                        else HALO_ISSUE_RES(3);
+#undef HALO_ISSUE_RES
                     } else {
                         if (nk == 4) issue_taps_streaming<R, S, X3, 4>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first, b_full, b_empty, bs, bphase, b_slots);
                         else if (nk == 2) issue_taps_streaming<R, S, X3, 2>(dbase, RB, npad, a_desc, b_desc0, a_half16, b_half16, b_slot16, idesc, idesc2, acc_first, b_full, b_empty, bs, bphase, b_slots);
@@ -459,7 +467,13 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     // tile striding.  Smallest modelled time wins; ties go to the smaller RB.
     double best_score = 0.0;
     int best_rb = 0, best_nstg = 0, best_res = 0;
+    static int force_rb = -1;   // experiments: MONKEY_B200_HALO_RB = 1 | 2 | 4 pins the row-block count
+    if (force_rb < 0) {
+        const char* e = getenv("MONKEY_B200_HALO_RB");
+        force_rb = e ? atoi(e) : 0;
+    }
     for (int rb = 1; rb <= 4; rb <<= 1) {
+        if (force_rb && rb != force_rb && !(rb == 1 && 2 * force_rb * (p.npad << p.x3) > 512)) continue;
         if (2 * rb * (p.npad << p.x3) > 512) break;                        // double-buffered accumulators in TMEM
         if (rb > 1 && 8 * (rb / 2) >= Ho) break;                           // the extra row-blocks would all be empty
         const int halo_rows = 8 * rb + R;                                   // (R-1) halo rows + 1 overrun row
@@ -498,6 +512,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
         mk_set_error("mk_conv2d_tc_halo: no shared-memory plan for this layer");
         return -2;
     }
+    (void)best_score;
     p.RB = best_rb;
     p.nstg = best_nstg;
     p.resident = best_res;

@@ -342,11 +342,15 @@ MK_EXPORT int mk_grid_sample_fwd(const float* inp, int B, int h, int w, int Cp, 
     MK_REQUIRE((long long)h * w * ld < (1LL << 31) && (long long)h * w * ldo < (1LL << 29),
                "mk_grid_sample_fwd: extent too large");
     const int cv = Cp / 4;
-    static int use_ca = -1;
-    if (use_ca < 0) {
+    // L1 allocation of the taps (cp.async.ca), measured on a B200 (L2 flushed, CUDA events): 3 ch x 256^2: 24.6 vs 26.6 us
+    // (better), 64 ch x 128^2: 36.0 vs 32.8 us, 128 ch x 64^2: 24.6 vs 21.7 us (worse: with 192 KB of staging buffers
+    // per SM the L1 is ~30 KB and thrashes) - so only the image-sized levels use it.  MONKEY_B200_GS_CA=0/1 forces.
+    static int force_ca = -2;
+    if (force_ca == -2) {
         const char* e = getenv("MONKEY_B200_GS_CA");
-        use_ca = (e && e[0] == '0') ? 0 : 1;
+        force_ca = e ? (e[0] == '0' ? 0 : 1) : -1;
     }
+    const int use_ca = force_ca >= 0 ? force_ca : (cv <= 2 ? 1 : 0);
     if (cv <= 32)
         return use_ca ? launch_gs_async<1, 3, true>(inp, B, h, w, Cp, ld, deform, d, h0, w0, mode, out, ldo, (cudaStream_t)stream)
                       : launch_gs_async<1, 3, false>(inp, B, h, w, Cp, ld, deform, d, h0, w0, mode, out, ldo, (cudaStream_t)stream);

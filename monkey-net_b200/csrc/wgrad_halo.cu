@@ -55,11 +55,14 @@ __device__ __forceinline__ uint64_t desc_mn(const void* smem, uint32_t lbo_bytes
 template <int S, int KS, bool X3>
 __device__ __forceinline__ void issue_chunk(uint32_t d0, int co_pad, uint64_t xa, uint64_t dy, uint64_t x_lo16,
                                             uint64_t dy_lo16, uint32_t idesc, uint32_t acc_first) {
+    // K-step outer, column tap inner: consecutive MMAs go to DIFFERENT accumulators.  Back-to-back MMAs into the same
+    // TMEM tile are dependent (accumulate) and, at N <= 128, each costs a fixed ~50 clk on top of its N/2 clk of math
+    // (80 clk measured for N = 48 whatever the kernel); interleaving the S independent accumulators lets them overlap.
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        const uint32_t d = d0 + (uint32_t)(s * co_pad);
+    for (int k = 0; k < KS; ++k) {
 #pragma unroll
-        for (int k = 0; k < KS; ++k) {
+        for (int s = 0; s < S; ++s) {
+            const uint32_t d = d0 + (uint32_t)(s * co_pad);
             const uint64_t a = xa + (uint64_t)(s * 8 + k * 64);   // + s pixel rows (128 B each), + 8 pixel rows per K step
             const uint64_t b = dy + (uint64_t)(k * 64);
             const uint32_t acc = k ? 1u : acc_first;
