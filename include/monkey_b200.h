@@ -270,6 +270,12 @@ int mk_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
 int mk_adam_flat(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                  long long* step, unsigned* ticket, int zero_grad, const float* lr_dev, void* stream);
 
+/* ---- data edge (frames_dataset.py:14-29): decoded uint8 image of T frames concatenated
+ * horizontally, `img` [H][T*w][Cs] (Cs = 1 gray, 2 gray+alpha, 3 RGB, 4 RGBA; DEVICE pointer) -> `dst` [T][H][w][Cp] fp32
+ * NHWC frames in [0,1]: gray replicated to RGB, alpha dropped, value/255 exactly as img_as_float32, channels 3..Cp-1
+ * zero.  The uint8 image is what crosses PCIe (4x fewer bytes than the reference's float32 frames). */
+int mk_stacked_u8_to_nhwc(const unsigned char* img, int H, int T, int w, int Cs, float* dst, int Cp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -501,9 +501,12 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
         // a streamed weight slot is consumed in (rb * K steps) MMAs but takes a full L2 round trip (~2800 clk) to
         // refill: with `bslots` slots in flight the ring sustains one slot per 2800 / bslots clk
         const double slot_clk = mma_clk / (R * S * p.nchunks);
-        const double ring_clk = res ? 0.0 : (2800.0 / bslots) * R * S * p.nchunks;
+        const double ring_clk = res ? 0.0 : (1500.0 / bslots) * R * S * p.nchunks;
         double t = mma_clk > l2 / 40.0 ? mma_clk : l2 / 40.0;
         if (ring_clk > t) t = ring_clk;
+        if (p.x3) t += 3000.0;   // 3xTF32: fixed cost of a super-tile (halo load -> split -> MMA chain, two stages deep);
+                                 // calibrated on the 4->64 and 48->48 layers, where RB = 2 measured 1.8x / 1.09x faster.
+                                 // In 1xTF32 RB = 1 with resident weights measured best on every layer tried.
         (void)slot_clk;
         const double score = t / rb * quant / rows_eff;
         if (!best_rb || score < best_score * 0.97) { best_rb = rb; best_score = score; best_nstg = nstg; best_res = res; }

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) k_stats_allreduce(const P2PP p) {
                                          par * P2P_MAX_WORLD + threadIdx.x;
         unsigned long long spins = 0;
         while (ld_acquire_sys(mine) < seq) {
-            if (++spins > (1ull << 31)) __trap();   // a peer that never arrives must abort, not hang the box
+            if (++spins > (1ull << 25)) __trap();   // ~20 s: a peer that never arrives must abort, not hang the box
         }
     }
     __syncthreads();

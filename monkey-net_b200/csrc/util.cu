@@ -289,3 +289,38 @@ MK_EXPORT int mk_gather_channels(const float* src, int lds, const int* map, floa
     k_gather_channels<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, lds, map, dst, ldd, npix, Cd);
     return mk_check_launch("mk_gather_channels");
 }
+
+// ------------------------------------------------------------------------------------------------ data edge
+// Stacked-frame image -> NHWC fp32 frames on the device: the reference decodes a video stored as ONE image of T frames
+// concatenated horizontally (frames_dataset.py:14-29: io.imread -> gray2rgb -> drop alpha -> img_as_float32 ->
+// moveaxis / reshape((-1,) + image_shape) / moveaxis) on the CPU and ships float32 to the GPU.  Here the decoded uint8
+// image goes over PCIe as it is (4x fewer bytes) and one kernel does the rest: frame split, gray -> RGB replication,
+// alpha drop, uint8 -> float32 /255 (IEEE division: bit-identical to img_as_float32), zero channel padding.
+__global__ void k_stacked_u8_to_nhwc(const unsigned char* __restrict__ img, int H, int T, int w, int Cs,
+                                     float* __restrict__ dst, int Cp, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w);
+        long long r = i / w;
+        const int h = (int)(r % H);
+        const int t = (int)(r / H);
+        const unsigned char* src = img + ((long long)h * T * w + (long long)t * w + x) * Cs;
+        float* o = dst + i * Cp;
+        const float c0 = (float)src[0] / 255.f;
+        const float c1 = Cs >= 3 ? (float)src[1] / 255.f : c0;   // gray (1 channel; 2 = gray + alpha) -> replicated
+        const float c2 = Cs >= 3 ? (float)src[2] / 255.f : c0;
+        o[0] = c0; o[1] = c1; o[2] = c2;
+        for (int c = 3; c < Cp; ++c) o[c] = 0.f;
+    }
+}
+
+MK_EXPORT int mk_stacked_u8_to_nhwc(const unsigned char* img, int H, int T, int w, int Cs, float* dst, int Cp,
+                                    void* stream) {
+    MK_REQUIRE(Cs >= 1 && Cs <= 4 && Cp >= 3, "mk_stacked_u8_to_nhwc: source channels 1..4, destination >= 3");
+    const long long total = (long long)T * H * w;
+    if (total == 0) return 0;
+    long long blocks = mk_cdiv(total, 256);
+    const long long cap = 16LL * mk_num_sms();
+    if (blocks > cap) blocks = cap;
+    k_stacked_u8_to_nhwc<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(img, H, T, w, Cs, dst, Cp, total);
+    return mk_check_launch("mk_stacked_u8_to_nhwc");
+}

@@ -1,0 +1,55 @@
+"""Data edge: stacked-frame videos onto the GPU.
+
+The reference's `frames_dataset.read_video` (frames_dataset.py:14-40) decodes a video stored as one PNG / JPG of T frames
+concatenated horizontally, converts it to float32 on the CPU (`img_as_float32`), reshuffles it into `(T, H, W, 3)` and
+only then hands float32 to the device.  Here the DECODED uint8 image crosses PCIe (4x fewer bytes) and one kernel
+(`mk_stacked_u8_to_nhwc`) splits the frames, replicates gray to RGB, drops alpha, divides by 255 exactly like
+`img_as_float32` and writes the NHWC layout the kernels consume.  Decoding the file itself (PIL, host) and the
+augmentation pipeline stay out of scope.
+"""
+import numpy as np
+import torch
+
+from . import lib
+
+
+def stacked_to_device(image_u8, frame_shape, device=None):
+    """`image_u8`: decoded stacked image, uint8 array / tensor `(H, T*w)` or `(H, T*w, C)` with C in 1..4 (host, ideally
+    pinned, or already on the device); `frame_shape` = the config's `image_shape` `(h, w, 3)`.
+    Returns `(video, nhwc)`: `video` is the reference-layout `(1, 3, T, H, W)` float32 view in [0, 1] (what
+    `FramesDataset` + the DataLoader deliver for a batch of one, frames_dataset.py:43-88), `nhwc` the backing
+    `[T][H][W][4]` buffer."""
+    t = torch.as_tensor(np.ascontiguousarray(image_u8) if isinstance(image_u8, np.ndarray) else image_u8)
+    if t.dtype != torch.uint8:
+        raise TypeError('stacked_to_device expects the decoded uint8 image, got %s' % t.dtype)
+    if t.dim() == 2:
+        t = t.unsqueeze(-1)
+    H, Wt, Cs = t.shape
+    h, w = int(frame_shape[0]), int(frame_shape[1])
+    if H != h or Wt % w:
+        raise ValueError('image %dx%d is not a horizontal stack of %dx%d frames' % (H, Wt, h, w))
+    T = Wt // w
+    device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+    if device.type != 'cuda':
+        raise RuntimeError('monkey-net_b200: stacked_to_device needs a CUDA device - the B200 path has no CPU fallback')
+    dev = t.to(device, non_blocking=True).contiguous()
+    nhwc = torch.empty(T, H, w, 4, dtype=torch.float32, device=device)
+    lib.call('mk_stacked_u8_to_nhwc', dev.data_ptr(), H, T, w, Cs, nhwc.data_ptr(), 4,
+             torch.cuda.current_stream(device).cuda_stream)
+    video = nhwc.view(1, T, H, w, 4).permute(0, 4, 1, 2, 3)[:, :3]
+    return video, nhwc
+
+
+def read_video_reference_semantics(image_u8, frame_shape):
+    """numpy restatement of frames_dataset.py:14-29 for a decoded stacked image (test oracle for the kernel):
+    gray2rgb -> drop alpha -> img_as_float32 -> moveaxis(1,0) -> reshape((-1,) + image_shape) -> moveaxis(1,2)."""
+    img = np.asarray(image_u8)
+    if img.ndim == 2:
+        img = img[..., None]
+    if img.shape[2] <= 2:
+        img = np.repeat(img[..., :1], 3, axis=2)
+    if img.shape[2] == 4:
+        img = img[..., :3]
+    img = img.astype(np.float32) / np.float32(255)
+    arr = np.moveaxis(img, 1, 0).reshape((-1,) + tuple(frame_shape))
+    return np.moveaxis(arr, 1, 2)
