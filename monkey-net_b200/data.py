@@ -42,7 +42,9 @@ def stacked_to_device(image_u8, frame_shape, device=None):
 
 def read_video_reference_semantics(image_u8, frame_shape):
     """numpy restatement of frames_dataset.py:14-29 for a decoded stacked image (test oracle for the kernel):
-    gray2rgb -> drop alpha -> img_as_float32 -> moveaxis(1,0) -> reshape((-1,) + image_shape) -> moveaxis(1,2)."""
+    gray2rgb -> drop alpha -> img_as_float32 -> moveaxis(1,0) -> reshape((-1,) + image_shape) -> moveaxis(1,2).
+    (The reference's reshape is only meaningful for SQUARE frames - every shipped config; the kernel implements the
+    frame split itself and agrees with this formula there.)"""
     img = np.asarray(image_u8)
     if img.ndim == 2:
         img = img[..., None]

@@ -10,7 +10,7 @@ def test_restatement_matches_the_reference_formula_on_a_decoded_png():
     from PIL import Image
     from monkey_net_b200 import data
     rng = np.random.default_rng(0)
-    T, h, w = 6, 16, 12
+    T, h, w = 6, 16, 16     # square frames: every shipped config (the reference's reshape only works for them)
     frames = rng.integers(0, 256, size=(T, h, w, 4), dtype=np.uint8)
     stacked = np.concatenate(list(frames), axis=1)                     # (h, T*w, 4): frames side by side
     buf = io.BytesIO()
