@@ -37,4 +37,4 @@ def test_ingested_video_feeds_the_modules():
         a = kp(video)
         b = kp(video.contiguous())
     assert a['mean'].shape == (1, 4, cfg['model_params']['common_params']['num_kp'], 2)
-    assert torch.equal(a['mean'], b['mean'])
+    assert float((a['mean'] - b['mean']).abs().max()) < 1e-6   # split-K atomics: equal up to summation order
