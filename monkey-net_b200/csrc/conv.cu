@@ -8,6 +8,7 @@
 // the same contract lives in conv_tc.cu; this file is the bit-faithful fp32 reference implementation on device
 // that the parity tests pin to the oracle at 1e-5.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 struct ConvP {
     const float* x; int N, Hin, Win, Hl, Wl, Cin_p, ldx, ups;
@@ -389,6 +390,20 @@ MK_EXPORT int mk_conv2d_wgrad(const float* x, int N, int Hin, int Win, int Cin_p
 
 // ------------------------------------------------------------------------------------------------ weight (un)packing
 // Parameter layout (Co, Ci/groups, 1, R, S) <-> GEMM layout [tap][Kin_p][Kout_p]; see include/monkey_b200.h.
+// cross operand of one weight (row = tap * Kout + ko of the K-major pack, ki = input channel, v = hi + remainder)
+__device__ __forceinline__ void pack_cross(__nv_bfloat16* cross, long long row, int ki, int Kin, float v, float hi) {
+    const int Kin8 = (Kin + 7) & ~7;
+    __nv_bfloat16* c = cross + (row * Kin8 + (ki & ~7)) * 2;
+    const int j = ki & 7;
+    c[j] = __float2bfloat16_rn(v);
+    c[8 + j] = __float2bfloat16_rn(v - hi);
+    if (ki + 4 >= Kin8) return;
+    if (ki + 4 >= Kin) {   // Kin = 8 q + 4: the last group holds 4 real channels, zero the other 4
+        c[j + 4] = __float2bfloat16_rn(0.f);
+        c[12 + j] = __float2bfloat16_rn(0.f);
+    }
+}
+
 __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int R, int S, int groups,
                               const int* __restrict__ cin_map, int Cin_p, int Cout_p, int mode,
                               float* __restrict__ wp, long long total, const float* __restrict__ bias,
@@ -397,7 +412,9 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
     if (bias_p && i < Cout_p) bias_p[i] = (bias && i < Co) ? bias[i] : 0.f;
     if (i >= total) return;
     // modes 2/3 = modes 0/1 in the tensor-core layout [tap][Kout][Kin] (K-major rows), values rounded to TF32;
-    // bit 3 (mode | 8): 3xTF32 pack - the TF32 remainder lo = rna(v - hi) follows the hi half at offset `total`
+    // bit 3 (mode | 8): reference-precision pack - behind the hi half (offset `total`) follows the CROSS operand of the
+    // BF16 correction MMA (conv_halo.cu): [tap][Kout][Kin rounded up to 8] 4-byte slots, every group of 8 input
+    // channels stored as 16 bf16 = [bf16(v) x8 | bf16(v - hi) x8]
     const int x3 = (mode >> 3) & 1;
     mode &= 7;
     const int tc = mode >> 1;
@@ -430,10 +447,7 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
         uint32_t u;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
         const float hi = __uint_as_float(u);
-        if (x3) {
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - hi));
-            wp[total + i] = __uint_as_float(u);
-        }
+        if (x3) pack_cross(reinterpret_cast<__nv_bfloat16*>(wp + total), (long long)tap * Kout + ko, ki, Kin, v, hi);
         v = hi;
     }
     wp[i] = v;
@@ -466,10 +480,7 @@ __global__ void k_pack_weight_ups(const float* __restrict__ w, int Co, int Ci, c
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
     const float hi = __uint_as_float(u);
     wp[i] = hi;
-    if (x3) {
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - hi));
-        wp[total + i] = __uint_as_float(u);
-    }
+    if (x3) pack_cross(reinterpret_cast<__nv_bfloat16*>(wp + total), t * Cout_p + co, ci_p, Cin_p, v, hi);
 }
 
 MK_EXPORT int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int groups, const int* cin_map,

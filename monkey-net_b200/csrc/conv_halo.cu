@@ -17,16 +17,22 @@
 //   * RESIDENT WEIGHTS.  CTAs are persistent (grid = #SMs x cout tiles, static tile striding).  When the packed weights
 //     of the CTA's cout tile fit ([tap][chunk][b_rows x 128 B] <= ~150 KB) they are loaded ONCE per CTA; otherwise they
 //     stream through a ring and the planner picks RB = 2 or 4 so one weight fetch feeds 2-4 accumulators.
-//   * 3xTF32 (mk_conv2d_tc_halo_x3).  Weights carry their lo half behind the hi half (mk_pack_weight mode | 8); the
-//     halo is split hi / lo in shared memory by two dedicated warps (same swizzled layout), and every K step issues
-//     A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same TMEM accumulator.
+//   * REFERENCE PRECISION (mk_conv2d_tc_halo_x3): TF32 main term + BF16 cross terms, 2 MMAs per K step.  With
+//     v = hi + lo (hi = rna_tf32(v)), a*b = a_hi*b_hi + (a_lo*b + a*b_lo) + O(2^-22).  The main term is one kind::tf32
+//     MMA (K = 8 channels).  The two cross terms are 2^-11 of the product, so 8 mantissa bits are enough for them
+//     (error 2^-20, the level of fp32 accumulation itself): ONE kind::f16 BF16 MMA (K = 16) whose K dimension is the
+//     concatenation  A' = [bf16(a_lo) x8 | bf16(a) x8],  B' = [bf16(b) x8 | bf16(b_lo) x8]  of the same 8 channels -
+//     32 bytes per row like the TF32 operand, same swizzled geometry, same descriptors.  The weights' cross operand is
+//     written by mk_pack_weight (mode | 16) behind the hi half; the halo's is produced in shared memory by four
+//     splitter warps.  Emulated error vs fp64 on random data: 6.6e-7 rms (fp32 matmul 2.7e-7, 3xTF32 7.8e-8,
+//     1xTF32 2.9e-4); cost 2 operand passes instead of the 3 of 3xTF32.
 //   * DOUBLE-BUFFERED TMEM.  2 x RB accumulators: the epilogue of tile t overlaps the MMAs of tile t+1.
 //   * TMA-STORE EPILOGUE.  tcgen05.ld (thread = pixel) -> bias / affine / residual / activation -> 128B-swizzled
 //     staging rows in shared memory -> cp.async.bulk.tensor store of {32 ch, TWv, 8} boxes: full-line writes, image /
 //     channel edges clipped by the TMA unit.  The residual tile is prefetched by its own TMA producer warp.
 //
 // Warp roles (352 threads): 0-3 = epilogue (TMEM lane quarter = warp), 4 = TMEM allocator + residual producer,
-// 5 = TMA producer (halo + weights), 6-7 and 9-10 = 3xTF32 splitters, 8 = MMA issuer.  The issuer has the highest warp id of
+// 5 = TMA producer (halo + weights), 6-7 and 9-10 = cross-operand splitters, 8 = MMA issuer.  The issuer has the highest warp id of
 // its scheduler (the arbiter is highest-wid-first) and its loop is fully unrolled over the filter taps (kernel
 // template <R, S, X3, RESIDENT>): with N = 48 an MMA retires in 24 clk, so the single issuing thread can afford only
 // a handful of instructions per MMA - the first version spent ~45 (runtime tap decode, 64-bit descriptor math, role
@@ -50,8 +56,8 @@ struct HP {
     int TWv, RB, tilesW, tilesH, ntiles;
     int halo_rows, a_half, a_stage, a_stages;
     int b_rows, b_half, b_slot, b_slots, resident;
-    int nchunks, ngroups, npad, acc_cols, tmem_cols;   // acc_cols = TMEM columns per accumulator (2 * npad in 3xTF32)
-    int x3, lo_tap_offset;
+    int nchunks, ngroups, npad, acc_cols, tmem_cols;   // acc_cols = TMEM columns per accumulator
+    int x3;
     int stg_bytes, nstg;   // nstg = 1 or 2 staging buffers (and as many residual buffers)
     const float* scale; const float* shift; int has_resid, act; float slope;
 };
@@ -98,8 +104,8 @@ __device__ __forceinline__ void issue_taps_resident(uint32_t d, int acc_cols, ui
                 const uint64_t a = a0 + (uint64_t)(rb * 1024);               // next row-block: + 8 image rows = 16 KB
                 const uint32_t dd = d + (uint32_t)(rb * acc_cols);
                 if (X3) {
-                    umma_tf32(dd, a + 2 * k, b + 2 * k, idesc2, acc);           // A_hi x [B_hi ; B_lo], N = 2 * b_rows
-                    umma_tf32(dd, a + a_half16 + 2 * k, b + 2 * k, idesc, 1u);  // A_lo x B_hi
+                    umma_tf32(dd, a + 2 * k, b + 2 * k, idesc, acc);                            // a_hi * b_hi
+                    umma_bf16(dd, a + a_half16 + 2 * k, b + b_half16 + 2 * k, idesc2, 1u);      // a_lo * b + a * b_lo
                 } else {
                     umma_tf32(dd, a + 2 * k, b + 2 * k, idesc, acc);
                 }
@@ -128,8 +134,8 @@ __device__ __forceinline__ void issue_taps_streaming(uint32_t dbase, int RB, int
 #pragma unroll 1
             for (int rb = 0; rb < RB; ++rb, a += 1024, d += (uint32_t)npad) {   // alternate the independent accumulators
                 if (X3) {
-                    umma_tf32(d, a + 2 * k, b + 2 * k, idesc2, acc);           // A_hi x [B_hi ; B_lo], N = 2 * b_rows
-                    umma_tf32(d, a + a_half16 + 2 * k, b + 2 * k, idesc, 1u);  // A_lo x B_hi
+                    umma_tf32(d, a + 2 * k, b + 2 * k, idesc, acc);
+                    umma_bf16(d, a + a_half16 + 2 * k, b + b_half16 + 2 * k, idesc2, 1u);
                 } else {
                     umma_tf32(d, a + 2 * k, b + 2 * k, idesc, acc);
                 }
@@ -143,7 +149,8 @@ __device__ __forceinline__ void issue_taps_streaming(uint32_t dbase, int RB, int
 template <int R, int S, bool X3, bool RES>
 __global__ void __launch_bounds__(H_THREADS, 1)
 k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR, const HP p) {
+            const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmY,
+            const __grid_constant__ CUtensorMap tmR, const HP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
@@ -172,6 +179,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 5 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB2) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
         if (p.has_resid) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
     }
@@ -221,7 +229,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         uint8_t* b = b_ring + bs * p.b_slot;
                         mbar_expect_tx(&b_full[bs], p.b_half << p.x3);
                         tma_load_3d(b, &tmB, &b_full[bs], ch * HK, cout0, tap);
-                        if (p.x3) tma_load_3d(b + p.b_half, &tmB, &b_full[bs], ch * HK, cout0, p.lo_tap_offset + tap);
+                        if (p.x3) tma_load_3d(b + p.b_half, &tmB2, &b_full[bs], ch * HK, cout0, tap);
                     }
                 }
             }
@@ -231,8 +239,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
             // Descriptors are kept as 64-bit values and advanced with plain adds (the 14-bit start-address field never
             // carries: shared memory is < 256 KB): the unrolled body is two 64-bit uniform adds + one UTCHMMA per MMA.
-            const uint32_t idesc = umma_idesc_tf32(128, X3 ? p.b_rows : ((n_this + 15) & ~15));
-            const uint32_t idesc2 = umma_idesc_tf32(128, 2 * p.b_rows);   // 3xTF32: [B_hi ; B_lo] as one N = 2 * b_rows operand
+            const uint32_t idesc = umma_idesc_tf32(128, (n_this + 15) & ~15);
+            const uint32_t idesc2 = umma_idesc_bf16(128, (n_this + 15) & ~15);   // cross terms: kind::f16, BF16 x BF16, K = 16
             const uint64_t a_desc0 = umma_desc(a_ring), b_desc0 = umma_desc(b_ring);
             const int RB = p.RB, nchunks = p.nchunks, a_stages = p.a_stages, b_slots = p.b_slots, npad = p.acc_cols;
             const uint64_t a_stage16 = (uint64_t)(p.a_stage >> 4), b_slot16 = (uint64_t)(p.b_slot >> 4);
@@ -300,19 +308,24 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else if (warp == 6 || warp == 7 || warp >= 9) {
-        // ===================================================================== 3xTF32 halo splitters (4 warps)
+        // ===================================================================== cross-operand splitters (4 warps)
+        // One 16-byte chunk (4 channels of one pixel row) per lane and piece, consecutive lanes on consecutive chunks
+        // (conflict-free).  The 8 channels of a K step are two chunks that the 128B swizzle keeps adjacent
+        // (chunk ^ (row & 7) flips only bit 0 inside the pair; odd rows hold them swapped) = lanes l and l ^ 1.
+        // In place: hi = rna_tf32(v).  Cross tile, same swizzled position: logical chunk 0 of the pair = bf16(v - hi)
+        // of the 8 channels, logical chunk 1 = bf16(v) of the 8 channels; the lane pair trades halves by shuffle.
         if (X3) {
             const int tid = (warp >= 9 ? warp - 7 : warp - 6) * 32 + lane;      // 0..127
-            const int n4 = p.a_half >> 4;
+            const int n4 = p.a_half >> 4;                                        // multiple of 128 (16 chunks x 8 rows)
             int ai = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
                 for (int ch = 0; ch < p.nchunks; ++ch, ++ai) {
                     const int as = ai % p.a_stages;
                     mbar_wait(&a_full[as], (ai / p.a_stages) & 1);
                     float4* hi = reinterpret_cast<float4*>(a_ring + as * p.a_stage);
-                    float4* lo = reinterpret_cast<float4*>(a_ring + as * p.a_stage + p.a_half);
-                    // four independent 16-byte pieces per thread and pass: the in-place hi store may alias the next
-                    // load as far as the compiler knows, so a one-piece loop runs at one shared-memory round trip each
+                    uint4* cr = reinterpret_cast<uint4*>(a_ring + as * p.a_stage + p.a_half);
+                    // four independent pieces per thread and pass (the in-place store may alias the next load as far
+                    // as the compiler knows: one piece per pass would run at one shared-memory round trip each)
                     for (int i0 = tid; i0 < n4; i0 += 512) {
                         float4 v[4];
 #pragma unroll
@@ -320,12 +333,19 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             if (i0 + 128 * j < n4) v[j] = hi[i0 + 128 * j];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (i0 + 128 * j < n4) {
-                                float4 h, l;
-                                split_tf32(v[j].x, h.x, l.x); split_tf32(v[j].y, h.y, l.y);
-                                split_tf32(v[j].z, h.z, l.z); split_tf32(v[j].w, h.w, l.w);
-                                hi[i0 + 128 * j] = h;
-                                lo[i0 + 128 * j] = l;
+                            const int i = i0 + 128 * j;
+                            if (i < n4) {                                         // warp-uniform (n4 % 128 == 0)
+                                float4 h;
+                                uint2 lo, top;
+                                split_cross(v[j], h, lo.x, lo.y, top.x, top.y);
+                                // this lane holds channels 0-3 of the K step iff chunk parity == row parity
+                                const bool first = ((i ^ (i >> 3)) & 1) == 0;
+                                uint2 send = first ? top : lo, recv;
+                                recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                                recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                                hi[i] = h;
+                                cr[i] = first ? make_uint4(lo.x, lo.y, recv.x, recv.y)      // bf16(v - hi), channels 0-7
+                                              : make_uint4(recv.x, recv.y, top.x, top.y);   // bf16(v), channels 0-7
                             }
                         }
                     }
@@ -369,13 +389,6 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     float v[32];
                     if (cn > 16) tmem_ld32(tacc + (uint32_t)cbase, v);
                     else tmem_ld16(tacc + (uint32_t)cbase, v);
-                    if (X3) {   // hi*lo partial products live in the second column half of the accumulator
-                        float u[32];
-                        if (cn > 16) tmem_ld32(tacc + (uint32_t)(p.npad + cbase), u);
-                        else tmem_ld16(tacc + (uint32_t)(p.npad + cbase), u);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] += u[j];
-                    }
                     if (valid) {
                         const float4* rrow = reinterpret_cast<const float4*>(rbuf + sb * p.stg_bytes + srow * 128);
                         float4* orow = reinterpret_cast<float4*>(sbuf + srow * 128);
@@ -445,7 +458,6 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     p.TWv = 16 - (S - 1);
     p.tilesW = (Wo + p.TWv - 1) / p.TWv;
     p.nchunks = (Cin_p + HK - 1) / HK;
-    p.lo_tap_offset = R * S;
     const int n_tile = Cout_p < 128 ? Cout_p : 128;
     p.b_rows = (n_tile + 15) & ~15;
     p.b_half = p.b_rows * 128;
@@ -461,7 +473,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     // K steps of one tap summed over the chunks, and the weight bytes one pass over all (tap, chunk) pairs fetches
     int ksteps = 0;
     for (int ch = 0; ch < p.nchunks; ++ch) ksteps += ((Cin_p - ch * HK > HK ? HK : Cin_p - ch * HK) + 7) >> 3;
-    const double w_bytes = (double)R * S * Cin_p * p.b_rows * 4 * (p.x3 ? 2 : 1);
+    const double w_bytes = (double)R * S * Cin_p * p.b_rows * 4 * (p.x3 ? 2 : 1);   // hi + cross operand
     // Planner: for RB in {1, 2, 4} and {2, 1} staging buffers find whether the weights can stay resident, and model the
     // time per 8-row block as max(MMA floor, L2->SM bytes / 40 B per clk) x the wave-quantisation loss of the static
     // tile striding.  Smallest modelled time wins; ties go to the smaller RB.
@@ -473,8 +485,8 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
         force_rb = e ? atoi(e) : 0;
     }
     for (int rb = 1; rb <= 4; rb <<= 1) {
-        if (force_rb && rb != force_rb && !(rb == 1 && 2 * force_rb * (p.npad << p.x3) > 512)) continue;
-        if (2 * rb * (p.npad << p.x3) > 512) break;                        // double-buffered accumulators in TMEM
+        if (force_rb && rb != force_rb && !(rb == 1 && 2 * force_rb * p.npad > 512)) continue;
+        if (2 * rb * p.npad > 512) break;                        // double-buffered accumulators in TMEM
         if (rb > 1 && 8 * (rb / 2) >= Ho) break;                           // the extra row-blocks would all be empty
         const int halo_rows = 8 * rb + R;                                   // (R-1) halo rows + 1 overrun row
         const int a_stage = (halo_rows * 16 * 128) << p.x3;
@@ -489,7 +501,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
             }
         }
         if (!nstg) break;
-        const double mma_clk = (double)rb * R * S * ksteps * (128.0 * p.b_rows / 256.0) * (p.x3 ? 3 : 1);
+        const double mma_clk = (double)rb * R * S * ksteps * (128.0 * p.b_rows / 256.0) * (p.x3 ? 2 : 1);
         const double a_bytes = (double)halo_rows * 16 * Cin_p * 4;
         const double l2 = a_bytes + (res ? 0.0 : w_bytes) + (double)rb * (1 + p.has_resid) * p.TWv * 8 * n_tile * 4;
         const long long tiles = (long long)p.tilesW * ((Ho + 8 * rb - 1) / (8 * rb)) * N;
@@ -548,7 +560,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     }
     if (p.a_stages > MAXA) p.a_stages = MAXA;
     MK_REQUIRE(p.a_stages >= 2 && (p.resident || p.b_slots >= 2), "mk_conv2d_tc_halo: ring plan failed");
-    p.acc_cols = p.npad << p.x3;
+    p.acc_cols = p.npad;
     const int cols = 2 * p.RB * p.acc_cols;
     p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
     const int smem_bytes = p.a_stages * p.a_stage + p.b_slots * p.b_slot + fixed;
@@ -565,7 +577,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     }
     EncodeTiledFn encode = get_encode();
     MK_REQUIRE(encode != nullptr, "mk_conv2d_tc_halo: cuTensorMapEncodeTiled unavailable");
-    CUtensorMap tmA, tmB, tmY, tmR;
+    CUtensorMap tmA, tmB, tmB2, tmY, tmR;
     cuuint32_t es4[4] = {1, 1, 1, 1};
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin_p, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
@@ -577,7 +589,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
         MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: activation tensor map rejected (%d)", (int)r);
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S * (p.x3 ? 2 : 1))};
+        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S)};
         cuuint64_t strides[2] = {(cuuint64_t)Cin_p * 4, (cuuint64_t)Cin_p * Cout_p * 4};
         cuuint32_t box[3] = {(cuuint32_t)HK, (cuuint32_t)p.b_rows, 1};
         cuuint32_t es[3] = {1, 1, 1};
@@ -585,6 +597,19 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
                             es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: weight tensor map rejected (%d)", (int)r);
+        tmB2 = tmB;
+        if (p.x3) {
+            // cross operand of the weights (mk_pack_weight mode | 16): [tap][Cout_p][Cin_p rounded up to 8] 4-byte slots
+            // (two bf16 each) behind the R*S*Cout_p*Cin_p floats of the hi half; moved as opaque 32-bit words
+            const cuuint64_t cin8 = (cuuint64_t)((Cin_p + 7) & ~7);
+            cuuint64_t dims2[3] = {cin8, (cuuint64_t)Cout_p, (cuuint64_t)(R * S)};
+            cuuint64_t strides2[2] = {cin8 * 4, cin8 * Cout_p * 4};
+            r = encode(&tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                       const_cast<float*>(wpack_tc) + (size_t)R * S * Cout_p * Cin_p, dims2, strides2, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: cross-operand tensor map rejected (%d)", (int)r);
+        }
     }
     for (int which = 0; which < 2; ++which) {
         if (which == 1 && !resid) { tmR = tmY; break; }
@@ -609,7 +634,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
             if (le == cudaSuccess) attr_done |= attr_bit;                                                            \
         }                                                                                                            \
         if (le == cudaSuccess)                                                                                       \
-            k_conv_halo<RR, SS, XX, RE><<<grid, H_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmY, tmR, p); \
+            k_conv_halo<RR, SS, XX, RE><<<grid, H_THREADS, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmB2, tmY, tmR, p); \
     } while (0)
 #define HALO_RS(XX, RE)                                  \
     do {                                                 \

@@ -18,12 +18,11 @@
 // * split-K (grid.z): layers whose tile count cannot fill 148 SMs (deep, low-resolution levels: 128 pixels x 1152 K)
 //   split the (tap, channel-chunk) loop over several CTAs that combine with red.global.add.v4.f32 into the
 //   zero-initialised output; split 0 carries the bias / residual.  Only for the linear epilogue (act == 0).
-// * 3xTF32 (mk_conv2d_tc_x3, "reference precision"): every fp32 operand is split hi + lo with hi = rna_tf32(v),
-//   lo = rna_tf32(v - hi) and the product is accumulated as A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same TMEM
-//   accumulator (the dropped lo*lo term is 2^-22 relative).  The weight pack carries its lo half behind the hi half
-//   (mk_pack_weight mode | 8); the ACTIVATION tile is split in shared memory by the four epilogue warps, idle during
-//   the main loop: hi written in place, lo into a second tile of the same swizzled layout (an elementwise map keeps
-//   the layout), published to the tensor core's async proxy with fence.proxy.async + a per-stage mbarrier.
+// * Reference precision (mk_conv2d_tc_x3): TF32 main term + BF16 cross terms, two MMAs per K step (scheme and error
+//   analysis in conv_halo.cu).  The weight pack carries its cross operand behind the hi half (mk_pack_weight mode | 8);
+//   the ACTIVATION tile is split in shared memory by the four epilogue warps, idle during the main loop: hi =
+//   rna_tf32(v) in place, [bf16(v - hi) x8 | bf16(v) x8] per K step into a second tile of the same swizzled layout,
+//   published to the tensor core's async proxy with fence.proxy.async + a per-stage mbarrier.
 // Same contract as mk_conv2d (conv.cu) for stride-1 convs without the pool option.
 #include "common.cuh"
 #include "../../include/monkey_b200.h"
@@ -46,13 +45,14 @@ struct TcP {
     int TW, TH, TN, tilesW, tilesH;
     int nstages, stage_bytes;  // smem ring: stage = A tile (16 KB) + B tile (b_rows x 128 B)
     int ksplit, iters_per_split, tmem_cols;
-    int x3, b_bytes, lo_tap_offset;  // 3xTF32: stage = A | B_hi | A_lo | B_lo ; lo weights at tap + lo_tap_offset
+    int x3, b_bytes;  // reference precision: stage = A_hi | B_hi | A_cross | B_cross
     const float* scale; const float* shift; const float* resid; int ldr, act; float slope;
     float* y;
 };
 
 __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtensorMap tmA,
-                                                 const __grid_constant__ CUtensorMap tmB, const TcP p) {
+                                                 const __grid_constant__ CUtensorMap tmB,
+                                                 const __grid_constant__ CUtensorMap tmB2, const TcP p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int STAGES = p.nstages, STAGE_BYTES = p.stage_bytes;
@@ -115,14 +115,13 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                 mbar_expect_tx(&full[stage], A_BYTES + (p.x3 ? 2 : 1) * p.b_bytes);
                 tma_load_4d(a, &tmA, &full[stage], ch * KC, w0 + s - pad_w, h0 + r - pad_h, n0);
                 tma_load_3d(a + A_BYTES, &tmB, &full[stage], ch * KC, cout0, tap0 + tap);
-                if (p.x3)
-                    tma_load_3d(a + 2 * A_BYTES + p.b_bytes, &tmB, &full[stage], ch * KC, cout0,
-                                p.lo_tap_offset + tap0 + tap);
+                if (p.x3) tma_load_3d(a + 2 * A_BYTES + p.b_bytes, &tmB2, &full[stage], ch * KC, cout0, tap0 + tap);
             }
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
         const uint32_t idesc = umma_idesc_tf32(BM, (n_this + 15) & ~15);  // rows beyond Cout_p are TMA zero fill
+        const uint32_t idesc_c = umma_idesc_bf16(BM, (n_this + 15) & ~15);
         for (int li = 0; li < niter; ++li) {
             const int stage = li % STAGES;
             const uint32_t phase = (li / STAGES) & 1;
@@ -136,12 +135,11 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
                 if (kleft > KC) kleft = KC;
                 const int nk = (kleft + 7) >> 3;  // UMMA K = 8 tf32 (32 bytes); the TMA zero-fills the ragged tail
                 if (p.x3) {
-                    const uint64_t aldesc = umma_desc(a + A_BYTES + p.b_bytes);
-                    const uint64_t bldesc = umma_desc(a + 2 * A_BYTES + p.b_bytes);
-                    for (int k = 0; k < nk; ++k) {   // small terms first, then the hi*hi product
-                        umma_tf32(tmem_base, aldesc + 2 * k, bdesc + 2 * k, idesc, (li | k) ? 1u : 0u);
-                        umma_tf32(tmem_base, adesc + 2 * k, bldesc + 2 * k, idesc, 1u);
-                        umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                    const uint64_t acdesc = umma_desc(a + A_BYTES + p.b_bytes);
+                    const uint64_t bcdesc = umma_desc(a + 2 * A_BYTES + p.b_bytes);
+                    for (int k = 0; k < nk; ++k) {   // a_hi * b_hi (TF32), then a_lo * b + a * b_lo (BF16, K = 16)
+                        umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (li | k) ? 1u : 0u);
+                        umma_bf16(tmem_base, acdesc + 2 * k, bcdesc + 2 * k, idesc_c, 1u);
                     }
                 } else
                 for (int k = 0; k < nk; ++k)      // advancing 32 B inside the 128 B swizzle row = +2 in 16 B units
@@ -152,21 +150,29 @@ __global__ void __launch_bounds__(256) k_conv_tc(const __grid_constant__ CUtenso
             __syncwarp();
         }
     } else if (warp >= 4) {
-        // ===================================================================== 3xTF32 operand split, then epilogue
+        // ===================================================================== operand split (x3), then epilogue
         if (p.x3) {
             const int tid = threadIdx.x - 128;
             for (int li = 0; li < niter; ++li) {
                 const int stage = li % STAGES;
                 mbar_wait(&full[stage], (li / STAGES) & 1);
                 float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + A_BYTES + p.b_bytes);
+                uint4* cr = reinterpret_cast<uint4*>(smem + stage * STAGE_BYTES + A_BYTES + p.b_bytes);
+                // one 16-byte chunk (4 channels) per lane and piece; the other 4 channels of the K step sit in the
+                // neighbouring chunk (lane ^ 1; the 128B swizzle swaps the pair in odd rows) - see conv_halo.cu
 #pragma unroll
-                for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-                    float4 v = hi[tid + 128 * i], h, l;
-                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                    hi[tid + 128 * i] = h;
-                    lo[tid + 128 * i] = l;
+                for (int k = 0; k < A_BYTES / 16 / 128; ++k) {
+                    const int i = tid + 128 * k;
+                    const float4 v = hi[i];
+                    float4 h;
+                    uint2 lo, top;
+                    split_cross(v, h, lo.x, lo.y, top.x, top.y);
+                    const bool first = ((i ^ (i >> 3)) & 1) == 0;   // this lane holds channels 0-3 of its K step
+                    uint2 send = first ? top : lo, recv;
+                    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                    hi[i] = h;
+                    cr[i] = first ? make_uint4(lo.x, lo.y, recv.x, recv.y) : make_uint4(recv.x, recv.y, top.x, top.y);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
                 __syncwarp();
@@ -260,7 +266,6 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     const int b_rows = Cout_p < BN_MAX ? (Cout_p + 15) & ~15 : BN_MAX;  // weight rows per stage = UMMA N
     p.x3 = t_x3;
     p.b_bytes = b_rows * KC * 4;
-    p.lo_tap_offset = R * S * (p.ups ? 4 : 1);
     p.stage_bytes = (p.x3 ? 2 : 1) * (A_BYTES + p.b_bytes);
     p.tmem_cols = b_rows <= 32 ? 32 : (b_rows <= 64 ? 64 : 128);
     const int grid_y = (Cout_p + BN_MAX - 1) / BN_MAX;
@@ -297,7 +302,7 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
     }
     EncodeTiledFn encode = get_encode();
     MK_REQUIRE(encode != nullptr, "mk_conv2d_tc: cuTensorMapEncodeTiled unavailable");
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmB2;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin_p, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)ldx * 4, (cuuint64_t)Win * ldx * 4, (cuuint64_t)Hin * Win * ldx * 4};
@@ -309,7 +314,8 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
         MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc: activation tensor map rejected (%d)", (int)r);
     }
     {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)(R * S * (p.ups ? 4 : 1) * (p.x3 ? 2 : 1))};
+        const int ntap = R * S * (p.ups ? 4 : 1);
+        cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)Cout_p, (cuuint64_t)ntap};
         cuuint64_t strides[2] = {(cuuint64_t)Cin_p * 4, (cuuint64_t)Cin_p * Cout_p * 4};
         cuuint32_t box[3] = {(cuuint32_t)KC, (cuuint32_t)b_rows, 1};
         cuuint32_t es[3] = {1, 1, 1};
@@ -317,6 +323,17 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
                             es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc: weight tensor map rejected (%d)", (int)r);
+        tmB2 = tmB;
+        if (p.x3) {   // cross operand behind the hi half: [tap][Cout_p][Cin_p rounded up to 8] 4-byte slots
+            const cuuint64_t cin8 = (cuuint64_t)((Cin_p + 7) & ~7);
+            cuuint64_t dims2[3] = {cin8, (cuuint64_t)Cout_p, (cuuint64_t)ntap};
+            cuuint64_t strides2[2] = {cin8 * 4, cin8 * Cout_p * 4};
+            r = encode(&tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                       const_cast<float*>(wpack_tc) + (size_t)ntap * Cout_p * Cin_p, dims2, strides2, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc: cross-operand tensor map rejected (%d)", (int)r);
+        }
     }
     static unsigned long long attr_done = 0;
     if (const unsigned long long attr_bit = mk_attr_needed(attr_done)) {
@@ -330,12 +347,12 @@ MK_EXPORT int mk_conv2d_tc(const float* x, int N, int Hin, int Win, int Cin_p, i
         if (e != cudaSuccess) { mk_set_error("mk_conv2d_tc memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
     dim3 grid((unsigned)(p.tilesW * p.tilesH * tilesN), (unsigned)grid_y, (unsigned)((p.ups ? 4 : 1) * p.ksplit));
-    k_conv_tc<<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, p);
+    k_conv_tc<<<grid, 256, smem_bytes, (cudaStream_t)stream>>>(tmA, tmB, tmB2, p);
     return mk_check_launch("mk_conv2d_tc");
 }
 
-// 3xTF32 variant (fp32-accurate tensor-core convolution): same contract, `wpack_tc` packed with mode | 8 (hi half
-// followed by the lo half).
+// Reference-precision variant (fp32-accurate tensor-core convolution): same contract, `wpack_tc` packed with mode | 8
+// (hi half followed by the cross operand).
 MK_EXPORT int mk_conv2d_tc_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
                               const float* wpack_tc, int R, int S, int pad, const float* scale, const float* shift,
                               const float* resid, int ldr, int act, float slope, float* y, int Cout_p, int ldy,

@@ -39,6 +39,24 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(v - hi));
     lo = __uint_as_float(l);
 }
+// Reference-precision operand split of 4 channels (see conv_halo.cu): hi = rna_tf32(v) in place, and for the BF16
+// cross-term MMA bf16(v - hi) and bf16(v), two channels per 32-bit word (lower channel in the low half)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_ch, float hi_ch) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_ch), "f"(lo_ch));
+    return r;
+}
+__device__ __forceinline__ float rna_tf32(float v) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    return __uint_as_float(h);
+}
+__device__ __forceinline__ void split_cross(const float4& v, float4& h, uint32_t& lo01, uint32_t& lo23, uint32_t& top01,
+                                            uint32_t& top23) {
+    h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+    lo01 = pack_bf16x2(v.x - h.x, v.y - h.y); lo23 = pack_bf16x2(v.z - h.z, v.w - h.w);   // v - hi is exact in fp32
+    top01 = pack_bf16x2(v.x, v.y); top23 = pack_bf16x2(v.z, v.w);
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -86,6 +104,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// kind::f16 with BF16 operands (K = 16 per instruction = 32 bytes per row, like K = 8 of kind::tf32), fp32 accumulate
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                  // D = F32
+    d |= 1u << 7;                  // A = BF16
+    d |= 1u << 10;                 // B = BF16
+    d |= (uint32_t)(n >> 3) << 17; // N
+    d |= (uint32_t)(m >> 4) << 24; // M
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }

@@ -12,8 +12,13 @@
 //     dW[(j, s)][ci = c][co]: a 3x3 layer fills 96 of the 128 MMA rows whatever its channel counts are, N = co is
 //     as narrow as the layer (N = 48 retires in 24 clk), and a (chunk, s) pair costs one MMA per 8 pixels;
 //   * the dY tile is loaded once per pixel tile (box {32 ch, 16 w, TR h}); its junk columns (col >= 16 - (S-1), whose
-//     shifted partners wrap into the next image row) are zeroed in shared memory by two helper warps, which in the
-//     3xTF32 mode also split both operands hi / lo in place (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi);
+//     shifted partners wrap into the next image row) are zeroed in shared memory by the helper warps.  In the
+//     reference-precision mode (mk_conv2d_wgrad_halo_x3; scheme and error analysis in conv_halo.cu) they also round
+//     both operands to TF32 in place and write the CROSS operands of the BF16 correction MMA: per pixel (128 B, the
+//     same offset as in the fp32 tile) two 64-byte K rows of 32 channels - X: [bf16(x - hi) | bf16(x)], dY:
+//     [bf16(dy) | bf16(dy - hi)] - an MN-major SWIZZLE_64B operand with the fp32 tile's LBO / SBO / K-step / tap-shift
+//     byte offsets (both swizzles XOR with address bits 7-8 = pixel & 3).  Per 8 pixels: one kind::tf32 MMA (K = 8)
+//     + one kind::f16 MMA (K = 16 rows = 8 pixels x {lo, top}) instead of the three of 3xTF32;
 //   * accumulates in TMEM across ALL pixel tiles of the CTA's range ((chunks x S) accumulators of co columns), one
 //     epilogue at the end: lane quarter q of the accumulator = tap row q, written (pixel splits: fp32 atomics) to the
 //     packed gradient [tap][Cin_p][Cout_p].
@@ -51,10 +56,13 @@ __device__ __forceinline__ uint64_t desc_mn(const void* smem, uint32_t lbo_bytes
     return d;
 }
 
+// layout-type field of the descriptor: SWIZZLE_128B_BASE32B (1) of the fp32 tiles -> SWIZZLE_64B (4) of the bf16 cross tiles
+constexpr uint64_t CROSS_FLIP = ((uint64_t)1 ^ (uint64_t)4) << 61;
+
 // all MMAs of one ci chunk for one pixel tile: S column taps x KS steps of 8 pixels, unrolled
 template <int S, int KS, bool X3>
 __device__ __forceinline__ void issue_chunk(uint32_t d0, int co_pad, uint64_t xa, uint64_t dy, uint64_t x_lo16,
-                                            uint64_t dy_lo16, uint32_t idesc, uint32_t acc_first) {
+                                            uint64_t dy_lo16, uint32_t idesc, uint32_t idesc_c, uint32_t acc_first) {
     // K-step outer, column tap inner: consecutive MMAs go to DIFFERENT accumulators.  Back-to-back MMAs into the same
     // TMEM tile are dependent (accumulate) and, at N <= 128, each costs a fixed ~50 clk on top of its N/2 clk of math
     // (80 clk measured for N = 48 whatever the kernel); interleaving the S independent accumulators lets them overlap.
@@ -67,9 +75,8 @@ __device__ __forceinline__ void issue_chunk(uint32_t d0, int co_pad, uint64_t xa
             const uint64_t b = dy + (uint64_t)(k * 64);
             const uint32_t acc = k ? 1u : acc_first;
             if (X3) {
-                umma_tf32(d, a + x_lo16, b, idesc, acc);
-                umma_tf32(d, a, b + dy_lo16, idesc, 1u);
-                umma_tf32(d, a, b, idesc, 1u);
+                umma_tf32(d, a, b, idesc, acc);                                               // x_hi * dy_hi
+                umma_bf16(d, (a + x_lo16) ^ CROSS_FLIP, (b + dy_lo16) ^ CROSS_FLIP, idesc_c, 1u);   // x_lo * dy + x * dy_lo
             } else {
                 umma_tf32(d, a, b, idesc, acc);
             }
@@ -152,9 +159,13 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             uint8_t* sb = smem + st * p.stage_bytes;
             uint8_t* dyb = sb + (p.x_region << (X3 ? 1 : 0));
             if (X3) {
+                // one 16-byte chunk (4 channels) per lane and piece, consecutive lanes on consecutive chunks; lanes l, l ^ 1
+                // hold the 8 channels of one 32-byte swizzle unit (the 32B-atom swizzle never splits it).  The even
+                // lane assembles the first 64-byte K row of the pixel, the odd lane the second one.
                 float4* hi = reinterpret_cast<float4*>(sb);
-                float4* lo = reinterpret_cast<float4*>(sb + p.x_region);
-                const int n4 = (nci * p.xa_half) >> 4;
+                uint4* cr = reinterpret_cast<uint4*>(sb + p.x_region);
+                const int n4 = (nci * p.xa_half) >> 4;                        // multiple of 128
+                const int odd = tid & 1;
                 for (int i0 = tid; i0 < n4; i0 += 512) {
                     float4 v[4];
 #pragma unroll
@@ -163,15 +174,21 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         if (i0 + 128 * j < n4) {
-                            float4 h, l;
-                            split_tf32(v[j].x, h.x, l.x); split_tf32(v[j].y, h.y, l.y);
-                            split_tf32(v[j].z, h.z, l.z); split_tf32(v[j].w, h.w, l.w);
-                            hi[i0 + 128 * j] = h;
-                            lo[i0 + 128 * j] = l;
+                            const int i = i0 + 128 * j;
+                            float4 h;
+                            uint2 lo, top;
+                            split_cross(v[j], h, lo.x, lo.y, top.x, top.y);
+                            uint2 send = odd ? lo : top, recv;
+                            recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                            recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                            hi[i] = h;
+                            // X: K row 0 = bf16(x - hi), K row 1 = bf16(x); 16-byte slot = the 32-byte unit's index
+                            cr[(i & ~7) + 4 * odd + ((i & 7) >> 1)] =
+                                odd ? make_uint4(recv.x, recv.y, top.x, top.y) : make_uint4(lo.x, lo.y, recv.x, recv.y);
                         }
                 }
                 float4* dhi = reinterpret_cast<float4*>(dyb);
-                float4* dlo = reinterpret_cast<float4*>(dyb + p.dy_region);
+                uint4* dcr = reinterpret_cast<uint4*>(dyb + p.dy_region);
                 const int m4 = (nco * p.dy_half) >> 4;
                 for (int i0 = tid; i0 < m4; i0 += 512) {
                     float4 v[4];
@@ -184,11 +201,16 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                             const int i = i0 + 128 * j;
                             const int pix = (i >> 3) & (TR * 16 - 1);       // 8 float4 per 128-byte pixel row
                             if ((pix & 15) >= p.TWv) v[j] = f4zero();
-                            float4 h, l;
-                            split_tf32(v[j].x, h.x, l.x); split_tf32(v[j].y, h.y, l.y);
-                            split_tf32(v[j].z, h.z, l.z); split_tf32(v[j].w, h.w, l.w);
+                            float4 h;
+                            uint2 lo, top;
+                            split_cross(v[j], h, lo.x, lo.y, top.x, top.y);
+                            uint2 send = odd ? top : lo, recv;
+                            recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                            recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
                             dhi[i] = h;
-                            dlo[i] = l;
+                            // dY: K row 0 = bf16(dy), K row 1 = bf16(dy - hi) (pairs with X's rows)
+                            dcr[(i & ~7) + 4 * odd + ((i & 7) >> 1)] =
+                                odd ? make_uint4(recv.x, recv.y, lo.x, lo.y) : make_uint4(top.x, top.y, recv.x, recv.y);
                         }
                 }
             } else {
@@ -213,6 +235,7 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         if (elect_one() && t1 > t0) {
             // M = 128 = 4 tap rows x 32 channels (a_major = b_major = MN), N = co_pad
             const uint32_t idesc = umma_idesc_tf32(128, p.co_pad) | (1u << 15) | (1u << 16);
+            const uint32_t idesc_c = umma_idesc_bf16(128, p.co_pad) | (1u << 15) | (1u << 16);
             const uint64_t x_lo16 = (uint64_t)(p.x_region >> 4), dy_lo16 = (uint64_t)(p.dy_region >> 4);
             const uint64_t xa16 = (uint64_t)(p.xa_half >> 4);
             int st = 0;
@@ -228,7 +251,7 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 uint32_t d = tmem_base;
 #pragma unroll 1
                 for (int c = 0; c < nci; ++c, xa += xa16, d += (uint32_t)(S * p.co_pad))
-                    issue_chunk<S, KS, X3>(d, p.co_pad, xa, dy, x_lo16, dy_lo16, idesc, acc_first);
+                    issue_chunk<S, KS, X3>(d, p.co_pad, xa, dy, x_lo16, dy_lo16, idesc, idesc_c, acc_first);
                 umma_commit(&empty[st]);
                 if (++st == p.stages) { st = 0; ph ^= 1; }
             }

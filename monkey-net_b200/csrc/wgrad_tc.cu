@@ -14,9 +14,11 @@
 //     layers (24 -> 24 @ 64x64 x 32 frames) took 150 us; now they are a single pass over X and dY.
 //   * only the 32-channel boxes that exist are staged (ceil(co/32) A boxes, ceil(ci/32) B boxes).  The MMA still runs
 //     M = 128: accumulator rows beyond the staged boxes are products of stale shared memory and are never read.
-//   * 3xTF32 (mk_conv2d_wgrad_tc_x3): both operands are activations, so both rings carry a lo half behind the hi half
-//     of every slot; the four epilogue warps split each landed slot in shared memory (hi in place, lo = rna(v - hi),
-//     same swizzled layout) and publish it through a_split / b_split mbarriers; the issuer runs lo*hi + hi*lo + hi*hi.
+//   * reference precision (mk_conv2d_wgrad_tc_x3; scheme in conv_halo.cu / wgrad_halo.cu): both operands are
+//     activations, so both rings carry a cross half behind the hi half of every slot; the four epilogue warps round
+//     each landed slot to TF32 in place and write per pixel two 64-byte bf16 K rows ([lo | top] for dY, [top | lo] for
+//     X: an MN-major SWIZZLE_64B operand with the fp32 box's offsets), published through a_split / b_split mbarriers;
+//     the issuer runs one kind::tf32 MMA + one kind::f16 (BF16, K = 16 rows = 8 pixels) MMA per 8 pixels.
 //   * grid = (co tiles, tap groups x ci tiles, pixel splits); splits combine with fp32 atomics (red) into the packed
 //     gradient, whose layout [tap][Cin_p][Cout_p] makes the epilogue's per-column writes coalesced across lanes.
 #include "tc_common.cuh"
@@ -35,7 +37,7 @@ struct WgTcP {
     int TW, TH, TN, tilesW, tilesH, nchunks, chunks_per_split, n_ci_tiles;
     int taps_per_cta, n_tap_groups, npad;   // npad = accumulator columns per tap (round16 of the ci tile)
     int na_max, nb_max, a_slots, b_slots, tmem_cols;
-    int x3;   // 3xTF32: slot = [hi boxes | lo boxes]
+    int x3;   // reference precision: slot = [hi boxes | cross boxes]
     float* dw;
 };
 
@@ -130,6 +132,7 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
         // ===================================================================== MMA issuer
         // M = 128 (co), N = round16(n_this) (ci), both operands MN-major; tap t accumulates at column t * npad
         const uint32_t idesc = umma_idesc_tf32(128, (n_this + 15) & ~15) | (1u << 15) | (1u << 16);
+        const uint32_t idesc_c = umma_idesc_bf16(128, (n_this + 15) & ~15) | (1u << 15) | (1u << 16);
         int bi = 0;
         for (int qi = 0; qi < nq; ++qi) {
             const int as = qi % p.a_slots;
@@ -143,13 +146,14 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
                     const uint64_t bdesc = umma_desc_mn(b_ring + bs * B_SLOT);
                     const uint32_t dcol = tmem_base + (uint32_t)(t * p.npad);
                     if (p.x3) {
-                        const uint64_t aldesc = umma_desc_mn(a_ring + as * A_SLOT + A_HALF);
-                        const uint64_t bldesc = umma_desc_mn(b_ring + bs * B_SLOT + B_HALF);
+                        // cross operands: same offsets, layout type SWIZZLE_128B_BASE32B (1) -> SWIZZLE_64B (4)
+                        constexpr uint64_t FLIP = ((uint64_t)1 ^ (uint64_t)4) << 61;
+                        const uint64_t acdesc = umma_desc_mn(a_ring + as * A_SLOT + A_HALF) ^ FLIP;
+                        const uint64_t bcdesc = umma_desc_mn(b_ring + bs * B_SLOT + B_HALF) ^ FLIP;
 #pragma unroll
                         for (int k = 0; k < PC / 8; ++k) {
-                            umma_tf32(dcol, aldesc + 64 * k, bdesc + 64 * k, idesc, (qi | k) ? 1u : 0u);
-                            umma_tf32(dcol, adesc + 64 * k, bldesc + 64 * k, idesc, 1u);
-                            umma_tf32(dcol, adesc + 64 * k, bdesc + 64 * k, idesc, 1u);
+                            umma_tf32(dcol, adesc + 64 * k, bdesc + 64 * k, idesc, (qi | k) ? 1u : 0u);
+                            umma_bf16(dcol, acdesc + 64 * k, bcdesc + 64 * k, idesc_c, 1u);
                         }
                     } else
 #pragma unroll
@@ -165,19 +169,27 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
             }
         }
     } else if (warp >= 4 && nq > 0) {
-        // ===================================================================== 3xTF32 operand split, then epilogue
+        // ===================================================================== operand split (x3), then epilogue
         if (p.x3) {
             const int tid = threadIdx.x - 128;
-            auto split_slot = [&](uint8_t* slot, int nboxes, int half) {
+            // lanes l, l ^ 1 hold the 8 channels of one 32-byte swizzle unit; the even lane assembles the pixel's first
+            // 64-byte K row, the odd lane the second one (A side: [lo | top], B side: [top | lo])
+            auto split_slot = [&](uint8_t* slot, int nboxes, int half, bool a_side) {
                 float4* hi = reinterpret_cast<float4*>(slot);
-                float4* lo = reinterpret_cast<float4*>(slot + half);
-                const int n4 = nboxes * (BOX_BYTES / 16);
+                uint4* cr = reinterpret_cast<uint4*>(slot + half);
+                const int n4 = nboxes * (BOX_BYTES / 16);       // multiple of 128
+                const int odd = tid & 1;
+                const bool lo_row = a_side ? !odd : odd;        // this lane assembles the bf16(v - hi) row
                 for (int i = tid; i < n4; i += 128) {
-                    float4 v = hi[i], h, l;
-                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                    float4 v = hi[i], h;
+                    uint2 lo, top;
+                    split_cross(v, h, lo.x, lo.y, top.x, top.y);
+                    uint2 send = lo_row ? top : lo, mine = lo_row ? lo : top, recv;
+                    recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                    recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
                     hi[i] = h;
-                    lo[i] = l;
+                    cr[(i & ~7) + 4 * odd + ((i & 7) >> 1)] =
+                        odd ? make_uint4(recv.x, recv.y, mine.x, mine.y) : make_uint4(mine.x, mine.y, recv.x, recv.y);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -186,12 +198,12 @@ __global__ void __launch_bounds__(256) k_wgrad_tc(const __grid_constant__ CUtens
             for (int qi = 0; qi < nq; ++qi) {
                 const int as = qi % p.a_slots;
                 mbar_wait(&a_full[as], (qi / p.a_slots) & 1);
-                split_slot(a_ring + as * A_SLOT, na, A_HALF);
+                split_slot(a_ring + as * A_SLOT, na, A_HALF, true);
                 if (lane == 0) mbar_arrive(&a_split[as]);
                 for (int t = 0; t < ntaps; ++t, ++bi) {
                     const int bs = bi % p.b_slots;
                     mbar_wait(&b_full[bs], (bi / p.b_slots) & 1);
-                    split_slot(b_ring + bs * B_SLOT, nb, B_HALF);
+                    split_slot(b_ring + bs * B_SLOT, nb, B_HALF, false);
                     if (lane == 0) mbar_arrive(&b_split[bs]);
                 }
             }

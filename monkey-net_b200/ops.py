@@ -96,6 +96,15 @@ def conv_mode():
 CONV_HALO = os.environ.get('MONKEY_B200_CONV_HALO', '1') != '0'
 
 
+def _tc_pack_numel(taps, kout, kin, x3):
+    """floats of a tensor-core weight pack [tap][Kout][Kin]; reference precision (mk_pack_weight mode | 8) appends the
+    cross operand of the BF16 correction MMA: [tap][Kout][Kin rounded up to 8] 4-byte slots (csrc/conv_halo.cu)"""
+    n = taps * kout * kin
+    if x3:
+        n += taps * kout * ((kin + 7) & ~7)
+    return n
+
+
 def _tc_launch(xp, N, Hin, Win, Cp, ups, wp, R, S, pad, scale, shift, resid_ptr, ldr, act, slope, yp, Cop, st, x3=False):
     """one tensor-core convolution launch on raw pointers: halo kernel when it takes the shape, else the per-tap one"""
     if CONV_HALO and not ups:
@@ -269,7 +278,7 @@ class _Conv(torch.autograd.Function):
         tc = _tc_ok(Cp, Cop, ups, pool, R, groups, mode)
         x3 = tc and mode == 'tf32x3'
         if tc:
-            wpack = _empty((16 if ups else R * S) * Cp * Cop * (2 if x3 else 1), like=x)
+            wpack = _empty(_tc_pack_numel(16 if ups else R * S, Cop, Cp, x3), like=x)
         lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop,
                  ((4 if ups else 2) | (8 if x3 else 0)) if tc else 0, wpack.data_ptr(), _ptr(bias), _ptr(bias_p), st)
         Hl, Wl = Hin << ups, Win << ups
@@ -313,7 +322,7 @@ class _Conv(torch.autograd.Function):
         tc = ctx.mode != 'fp32'
         x3 = ctx.mode == 'tf32x3'
         if ctx.needs_input_grad[0]:
-            wt = _empty(R * S * Cop * Cp * (2 if x3 else 1), like=x)
+            wt = _empty(_tc_pack_numel(R * S, Cp, Cop, x3) if tc else R * S * Cop * Cp, like=x)
             lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop,
                      (3 | (8 if x3 else 0)) if tc else 1, wt.data_ptr(), None, None, st)
             dx = _empty(N, Hin, Win, Cp, like=x)
@@ -415,7 +424,7 @@ def _infer_pack(weight, bias, segs, groups, ups, norm, Cp, tc, x3=False):
     Cop = pad4(Co)
     st = _stream()
     cmap, _ = _channel_maps(segs, weight.device)
-    wpack = _empty((16 if (tc and ups) else R * S) * Cp * Cop * (2 if x3 else 1), like=weight)
+    wpack = _empty(_tc_pack_numel(16 if ups else R * S, Cop, Cp, x3) if tc else R * S * Cp * Cop, like=weight)
     bias_p = _empty(Cop, like=weight) if bias is not None else None
     lib.call('mk_pack_weight', weight.data_ptr(), Co, Cig, R, S, groups, _ptr(cmap), Cp, Cop,
              ((4 if ups else 2) | (8 if x3 else 0)) if tc else 0, wpack.data_ptr(), _ptr(bias), _ptr(bias_p), st)

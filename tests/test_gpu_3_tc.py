@@ -65,7 +65,7 @@ def _run_conv_kernel(kernel, x, w, b, k, pad, r, act, ups=0):
     Ho, Wo = Hl + 2 * pad - k + 1, Wl + 2 * pad - k + 1
     x3 = kernel == 'tf32x3'
     taps = (16 if ups else k * k) if kernel != 'ffma' else k * k
-    wp = torch.empty(taps * cin * cout * (2 if x3 else 1), device=dev)
+    wp = torch.empty(taps * cout * (cin + (((cin + 7) & ~7) if x3 else 0)), device=dev)
     bp = torch.empty(cout, device=dev)
     mode = 0 if kernel == 'ffma' else ((4 if ups else 2) | (8 if x3 else 0))
     lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, mode, wp.data_ptr(),
@@ -293,7 +293,7 @@ def test_conv_halo_matches_torch_conv2d(cin, cout, k, pad, H, W, N, resid, act, 
     Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
     r = torch.randn(N, Ho, Wo, cout, device=dev) if resid else None
     x3 = kernel == 'halo_x3'
-    wp = torch.empty(k * k * cin * cout * (2 if x3 else 1), device=dev)
+    wp = torch.empty(k * k * cout * (cin + (((cin + 7) & ~7) if x3 else 0)), device=dev)
     bp = torch.empty(cout, device=dev)
     lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, 2 | (8 if x3 else 0), wp.data_ptr(),
              b.data_ptr(), bp.data_ptr(), st)

@@ -38,7 +38,7 @@ def main():
         hbm_us = 4.0 * (x.numel() + y.numel() * (2 if resid else 1)) / 6.568e12 * 1e6
         res = []
         for x3 in (0, 1):
-            wt = torch.empty(k * k * cin * cout * (2 if x3 else 1), device=dev)
+            wt = torch.empty(k * k * cout * (cin + (((cin + 7) & ~7) if x3 else 0)), device=dev)
             lib.call('mk_pack_weight', w.data_ptr(), cout, cin, k, k, 1, None, cin, cout, 2 | (8 if x3 else 0),
                      wt.data_ptr(), None, None, st)
             rp, ldr = (r.data_ptr(), cout) if resid else (None, 0)
