@@ -276,6 +276,9 @@ HALO_CASES = [
     (48, 48, 3, 1, 61, 50, 10, True, 1),      # H, W not multiples of the tile
     (128, 32, 3, 1, 64, 64, 8, False, 0),     # 36 resident weight slots
     (36, 12, 3, 1, 64, 64, 16, False, 0),     # hourglass head: Cout_p = 12 (one 16-column accumulator)
+    (64, 16, 4, 3, 61, 61, 8, False, 0),      # column taps on N: 4 x 16 = 64 accumulator columns, full correlation
+    (32, 64, 3, 1, 40, 40, 4, False, 2),      # column taps on N: 3 x 64 = 192 columns, two output groups, sigmoid
+    (16, 64, 4, 0, 35, 35, 6, True, 1),       # column taps on N at the limit N = 256, residual
 ]
 
 

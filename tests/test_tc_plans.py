@@ -99,9 +99,12 @@ def test_every_layer_has_a_valid_tensor_core_plan(name, res, batch):
                         gx, gy, rb, smem, a_st, b_sl, resident, tmem, ntiles, halo_rows, a_stage, b_slot, twv, ngr, npad, fl = o
                         assert k_ in (1, 3, 4) and smem <= 227 * 1024 and 2 <= a_st <= 4 and rb in (1, 2, 4)
                         assert 2 * rb * npad <= tmem <= 512 and halo_rows == 8 * rb + k_ and twv == 17 - k_
-                        assert (resident and b_sl == k_ * k_ * ((ci_ + 31) // 32) <= 40) or (not resident and 2 <= b_sl <= 8)
-                        assert gx * gy <= 148 and ntiles >= gx and (fl & 1) == x3 and (fl >> 1) in (1, 2)
-                        nstg = fl >> 1
+                        ct = (fl >> 3) & 1     # column taps stacked on N: one weight slot per tap ROW, RB = 1
+                        assert not ct or (rb == 1 and k_ > 1 and co_ % 16 == 0 and npad == k_ * co_ <= 256)
+                        nslots = (k_ if ct else k_ * k_) * ((ci_ + 31) // 32)
+                        assert (resident and b_sl == nslots <= 40) or (not resident and 2 <= b_sl <= 8)
+                        assert gx * gy <= 148 and ntiles >= gx and (fl & 1) == x3 and ((fl >> 1) & 3) in (1, 2)
+                        nstg = (fl >> 1) & 3
                         assert a_st * a_stage + b_sl * b_slot + nstg * (1 + res_) * twv * 8 * 128 + 2048 == smem
                 rc, o = plan(lib, 'mk_conv2d_wgrad_halo_plan', N, H, W, cin_p, cop, k, k, pad, x3)
                 assert rc in (0, -2), (name, 'wgrad halo', lib.mk_last_error())
