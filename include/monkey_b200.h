@@ -203,12 +203,16 @@ int mk_resize_bwd(const float* dout, int N, int h, int w, int Cp, int ldo, int m
 /* ---- keypoint head: softmax(heat/T) over H*W + gaussian2kp (keypoint_detector.py:43-78,101-107) ----------------
  * logits [N][H][W][ld] (K logical channels).  mean [N][K][2], var [N][K][4] (row-major 2x2) ==
  * (B,D,K,2)/(B,D,K,2,2) contiguous.  var_mode 0 'matrix', 1 'single' (var [N][K][1]).  clip <= 0: no clip_variance.
- * aux [N][K][8]: softmax max, sum-exp, raw (unclipped) covariance (4), spare - saved for backward. */
+ * aux [N][K][8]: softmax max, sum-exp, raw (unclipped) covariance (4), spare - saved for backward.
+ * scratch: *out of mk_kp_head_scratch_floats(N, H, W, K, out) floats of device memory for the chunk partials of the
+ * many-block kernels (all channels of a pixel chunk per block; partials combined in a fixed order); NULL selects the
+ * one-block-per-(frame, keypoint) kernels. */
+int mk_kp_head_scratch_floats(int N, int H, int W, int K, long long* out /* host */);
 int mk_kp_head_fwd(const float* logits, int N, int H, int W, int K, int ld, float inv_temperature, int var_mode,
-                   float clip, float* mean, float* var, float* aux, void* stream);
+                   float clip, float* mean, float* var, float* aux, float* scratch, void* stream);
 int mk_kp_head_bwd(const float* logits, int N, int H, int W, int K, int ld, float inv_temperature, int var_mode,
                    float clip, const float* mean, const float* aux, const float* dmean, const float* dvar,
-                   float* dlogits /* [N][H][W][ld], pads zeroed inside */, void* stream);
+                   float* dlogits /* [N][H][W][ld], pads zeroed inside */, float* scratch, void* stream);
 
 /* ---- movement embedding (movement_embedding.py:42-92) incl. kp2gaussian (keypoint_detector.py:7-40) ------------
  * flags bit0 use_heatmap, bit1 use_difference, bit2 use_deformed_source_image, bit3 add_bg_feature_map,

@@ -42,8 +42,9 @@
 //     col >= TWv are exactly the lanes that would wrap), i.e. S - 1 shuffles per output value.  3x3, Cout 48:
 //     3 x (128 + 144) operand rows per K step instead of 9 x (128 + 48).
 //
-// Warp roles (352 threads): 0-3 = epilogue (TMEM lane quarter = warp), 4 = TMEM allocator + residual producer,
-// 5 = TMA producer (halo + weights), 6-7 and 9-10 = cross-operand splitters, 8 = MMA issuer.  The issuer has the highest warp id of
+// Warp roles (384 threads): 0-3 = epilogue (TMEM lane quarter = warp), 4 = TMEM allocator + residual producer,
+// 5 = TMA producer (halo, resident weights), 11 = TMA producer of streamed weights, 6-7 and 9-10 = cross-operand
+// splitters, 8 = MMA issuer.  The issuer has the highest warp id of
 // its scheduler (the arbiter is highest-wid-first) and its loop is fully unrolled over the filter taps (kernel
 // template <R, S, X3, RESIDENT>): with N = 48 an MMA retires in 24 clk, so the single issuing thread can afford only
 // a handful of instructions per MMA - the first version spent ~45 (runtime tap decode, 64-bit descriptor math, role
@@ -60,7 +61,7 @@ using namespace mk_tc;
 constexpr int HK = 32;                 // fp32 channels per chunk = 128 bytes
 constexpr int MAXA = 4, MAXB = 40;     // ring depth bounds (MAXB also bounds the resident slots: 9 taps x 4 chunks = 36)
 constexpr int H_SMEM_MAX = 227 * 1024;
-constexpr int H_THREADS = 352;
+constexpr int H_THREADS = 384;
 
 struct HP {
     int N, Ho, Wo, Cout_p, Cin_p, R, S, pad;
@@ -69,7 +70,7 @@ struct HP {
     int b_rows, b_half, b_tx, b_slot, b_slots, resident;   // b_tx = bytes one weight TMA box delivers
     int nchunks, ngroups, npad, acc_cols, tmem_cols;   // acc_cols = TMEM columns per accumulator
     int x3, ct;            // ct: column taps stacked on N (b_rows = round16(S * Cout_p), one weight slot per tap ROW)
-    int stg_bytes, nstg;   // nstg = 1 or 2 staging buffers (and as many residual buffers)
+    int stg_bytes, nstg;   // nstg = 1..3 staging buffers (and as many residual buffers)
     const float* scale; const float* shift; int has_resid, act; float slope;
 };
 
@@ -178,8 +179,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* tmem_full = b_empty + MAXB;
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* r_full = tmem_empty + 2;
-    uint64_t* r_empty = r_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + 2);
+    uint64_t* r_empty = r_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cout0 = blockIdx.y * 128;
@@ -198,10 +199,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 8 && lane == 0) {
         for (int i = 0; i < MAXA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_split[i], 4); }
         for (int i = 0; i < MAXB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
-            mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 4);
-        }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
@@ -216,9 +215,12 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 5) {
-        // ===================================================================== TMA producer: halo + weights
+        // ===================================================================== TMA producer: halo (+ resident weights)
+        // Streamed weights have their own producer (warp 11): one thread serving both rings in order issued the next
+        // chunk's halo only after the last weight slot of the current chunk had found a free ring entry, i.e. a few
+        // taps before the MMAs needed it - ncu showed the issuer waiting 30 % of its time for the split halo.
         if (elect_one()) {
-            int ai = 0, bi = 0;
+            int ai = 0;
             for (int tile = blockIdx.x, lt = 0; tile < p.ntiles; tile += gridDim.x, ++lt) {
                 const int n = tile / tiles_per_img, trem = tile - n * tiles_per_img;
                 const int th = trem / p.tilesW, tw = trem - th * p.tilesW;
@@ -228,16 +230,9 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(&a_empty[as], ((ai / p.a_stages) & 1) ^ 1);
                     mbar_expect_tx(&a_full[as], p.a_half);
                     tma_load_4d(a_ring + as * p.a_stage, &tmA, &a_full[as], ch * HK, w0 - p.pad, h0 - p.pad, n);
-                    if (p.resident && lt > 0) continue;
+                    if (!p.resident || lt > 0) continue;
                     for (int tap = 0; tap < ntaps; ++tap) {
-                        int bs;
-                        if (p.resident) {
-                            bs = ch * ntaps + tap;
-                        } else {
-                            bs = bi % p.b_slots;
-                            mbar_wait(&b_empty[bs], ((bi / p.b_slots) & 1) ^ 1);
-                            ++bi;
-                        }
+                        const int bs = ch * ntaps + tap;
                         uint8_t* b = b_ring + bs * p.b_slot;
                         mbar_expect_tx(&b_full[bs], p.b_tx << p.x3);
                         tma_load_3d(b, &tmB, &b_full[bs], ch * HK, cout0, CT ? tap * p.S : tap);
@@ -245,6 +240,21 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                 }
             }
+        }
+    } else if (warp == 11) {
+        // ===================================================================== TMA producer: streamed weights
+        if (!p.resident && elect_one()) {
+            int bi = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x)
+                for (int ch = 0; ch < p.nchunks; ++ch)
+                    for (int tap = 0; tap < ntaps; ++tap, ++bi) {
+                        const int bs = bi % p.b_slots;
+                        mbar_wait(&b_empty[bs], ((bi / p.b_slots) & 1) ^ 1);
+                        uint8_t* b = b_ring + bs * p.b_slot;
+                        mbar_expect_tx(&b_full[bs], p.b_tx << p.x3);
+                        tma_load_3d(b, &tmB, &b_full[bs], ch * HK, cout0, CT ? tap * p.S : tap);
+                        if (p.x3) tma_load_3d(b + p.b_half, &tmB2, &b_full[bs], ch * HK, cout0, CT ? tap * p.S : tap);
+                    }
         }
     } else if (warp == 8) {
         // ===================================================================== MMA issuer (one elected thread)
@@ -313,14 +323,14 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int w0 = tw * p.TWv, h0 = th * 8 * p.RB;
                 for (int rb = 0; rb < p.RB; ++rb)
                     for (int g = 0; g < ngroups; ++g, ++gi) {
-                        const int sb = p.nstg == 2 ? (gi & 1) : 0;
-                        mbar_wait(&r_empty[sb], ((p.nstg == 2 ? gi >> 1 : gi) & 1) ^ 1);
+                        const int sb = gi % p.nstg;
+                        mbar_wait(&r_empty[sb], ((gi / p.nstg) & 1) ^ 1);
                         mbar_expect_tx(&r_full[sb], p.stg_bytes);
                         tma_load_4d(rbuf + sb * p.stg_bytes, &tmR, &r_full[sb], cout0 + g * 32, w0, h0 + 8 * rb, n);
                     }
             }
         }
-    } else if (warp == 6 || warp == 7 || warp >= 9) {
+    } else if (warp == 6 || warp == 7 || warp == 9 || warp == 10) {
         // ===================================================================== cross-operand splitters (4 warps)
         // One 16-byte chunk (4 channels of one pixel row) per lane and piece, consecutive lanes on consecutive chunks
         // (conflict-free).  The 8 channels of a K step are two chunks that the 128B swizzle keeps adjacent
@@ -387,7 +397,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int rb = 0; rb < p.RB; ++rb) {
                 const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * p.RB + rb) * p.acc_cols);
                 for (int g = 0; g < ngroups; ++g, ++gi) {
-                    const int sb = p.nstg == 2 ? (gi & 1) : 0;
+                    const int sb = gi % p.nstg;
                     uint8_t* sbuf = stg + sb * p.stg_bytes;
                     if (p.nstg == 1) {
                         // single staging buffer: the store issued one group ago must have finished reading it
@@ -396,7 +406,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                     // (two buffers: sbuf was handed to the TMA store two groups ago, and the leader waited for that
                     //  read to complete BEFORE the barrier of the previous group - one barrier per group suffices)
-                    if (p.has_resid) mbar_wait(&r_full[sb], (p.nstg == 2 ? gi >> 1 : gi) & 1);
+                    if (p.has_resid) mbar_wait(&r_full[sb], (gi / p.nstg) & 1);
                     const int cbase = g * 32;
                     const int cn = min(32, n_this - cbase);           // multiple of 4
                     float v[32];
@@ -441,7 +451,10 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> TMA store reads
                     __syncwarp();
                     if (p.has_resid && lane == 0) mbar_arrive(&r_empty[sb]);       // residual buffer consumed
+                    // the buffer written by the NEXT group must have been read by its store (nstg groups ago): with
+                    // two buffers that is the store issued one group ago, with three the one before it
                     if (leader && p.nstg == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    if (leader && p.nstg == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     epi_bar();
                     if (leader) {
                         tma_store_4d(&tmY, sbuf, cout0 + cbase, w0, h0 + 8 * rb, n);
@@ -467,13 +480,32 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }  // namespace
 
 static thread_local int t_hx3 = 0;
+static thread_local int t_hct = 0;   // column-taps-on-N requested for this call (set by the exported entry point)
 static thread_local int* t_hplan = nullptr;
+
+// Column taps on N pay when the MMA phase of the plain schedule outweighs the epilogue: CT divides the operand rows
+// read per K step by ~2 (3x3) but reads S accumulator column groups per output group and forces RB = 1.  Constants
+// measured on B200 (profiles/r2_conv_micro_v8_ct_on.txt): UTCHMMA = 18 + 0.35 * (M + N) clk, epilogue ~2600 clk per
+// 32-channel group of a 128-pixel tile.  MONKEY_B200_HALO_CT = 0 never, 2 whenever eligible (experiments).
+static bool halo_wants_ct(int R, int S, int Cin_p, int Cout_p, int x3) {
+    static int ct_env = -1;
+    if (ct_env < 0) {
+        const char* e = getenv("MONKEY_B200_HALO_CT");
+        ct_env = e ? atoi(e) : 1;
+    }
+    if (!ct_env || S <= 1 || Cout_p > 128 || Cout_p % 16 || S * Cout_p > 256) return false;
+    if (ct_env == 2) return true;
+    const int ksteps = (Cin_p + 7) / 8;
+    const double mma_plain = (double)R * S * ksteps * (18.0 + 0.35 * (128 + Cout_p)) * (x3 ? 2 : 1);
+    const double epilogue = 2600.0 * ((Cout_p + 31) / 32);
+    return mma_plain > 1.2 * epilogue;
+}
 
 // Returns 0 on success, -2 when the shape is outside this kernel's envelope or the launch would leave most SMs idle
 // (callers use mk_conv2d_tc, whose split-K serves the few-tile layers).
-MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc,
-                                int R, int S, int pad, const float* scale, const float* shift, const float* resid,
-                                int ldr, int act, float slope, float* y, int Cout_p, int ldy, void* stream) {
+static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc,
+                          int R, int S, int pad, const float* scale, const float* shift, const float* resid,
+                          int ldr, int act, float slope, float* y, int Cout_p, int ldy, void* stream) {
     const int Ho = Hin + 2 * pad - R + 1, Wo = Win + 2 * pad - S + 1;
     if (Cin_p % 4 || ldx % 4 || Cout_p % 4 || ldy % 4 || (resid && ldr % 4) || R != S || (R != 1 && R != 3 && R != 4) ||
         Ho < 1 || Wo < 1) {
@@ -487,13 +519,7 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
     p.tilesW = (Wo + p.TWv - 1) / p.TWv;
     p.nchunks = (Cin_p + HK - 1) / HK;
     const int n_tile = Cout_p < 128 ? Cout_p : 128;
-    // column taps stacked on N (see the header): narrow layers whose S weight tiles fit one N <= 256 operand
-    static int ct_env = -1;   // experiments: MONKEY_B200_HALO_CT = 0 switches the mode off
-    if (ct_env < 0) {
-        const char* e = getenv("MONKEY_B200_HALO_CT");
-        ct_env = e ? atoi(e) : 1;
-    }
-    p.ct = (ct_env && S > 1 && Cout_p <= 128 && Cout_p % 16 == 0 && S * Cout_p <= 256) ? 1 : 0;
+    p.ct = t_hct;   // column taps stacked on N (see the header); eligibility checked by halo_wants_ct
     p.b_rows = p.ct ? S * Cout_p : ((n_tile + 15) & ~15);
     p.b_half = p.b_rows * 128;
     p.b_tx = p.b_half;
@@ -528,10 +554,21 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
         const int halo_rows = 8 * rb + R;                                   // (R-1) halo rows + 1 overrun row
         const int a_stage = (halo_rows * 16 * 128) << p.x3;
         int nstg = 0, res = 0, bslots = 0;
-        for (int ns = 2; ns >= 1 && !nstg; --ns) {
+        static int max_nstg = -1;   // experiments: MONKEY_B200_HALO_NSTG caps the staging buffers (default 3)
+        if (max_nstg < 0) {
+            const char* e = getenv("MONKEY_B200_HALO_NSTG");
+            max_nstg = e ? atoi(e) : 3;
+            if (max_nstg < 1 || max_nstg > 3) max_nstg = 3;
+        }
+        // resident weights with as many staging buffers as fit (3: every TMA store has two group times to drain)...
+        for (int ns = max_nstg; ns >= 1 && !nstg; --ns) {
             const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + 2048;
             if (nB <= MAXB && nB * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) { nstg = ns; res = 1; bslots = nB; }
-            else if ((ns == 1 ? 2 : 3) * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) {
+        }
+        // ...else a weight ring, where shared memory buys ring depth before a third staging buffer
+        for (int ns = max_nstg < 2 ? max_nstg : 2; ns >= 1 && !nstg; --ns) {
+            const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + 2048;
+            if ((ns == 1 ? 2 : 3) * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) {
                 nstg = ns; res = 0;
                 bslots = (H_SMEM_MAX - fixed - 2 * a_stage) / p.b_slot;
                 if (bslots > 8) bslots = 8;
@@ -686,6 +723,21 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
 #undef HALO_LAUNCH
     if (le != cudaSuccess) { mk_set_error("mk_conv2d_tc_halo: smem attribute: %s", cudaGetErrorString(le)); return (int)le; }
     return mk_check_launch("mk_conv2d_tc_halo");
+}
+
+MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc,
+                                int R, int S, int pad, const float* scale, const float* shift, const float* resid,
+                                int ldr, int act, float slope, float* y, int Cout_p, int ldy, void* stream) {
+    t_hct = (R == S && halo_wants_ct(R, S, Cin_p, Cout_p, t_hx3)) ? 1 : 0;
+    int rc = halo_conv_impl(x, N, Hin, Win, Cin_p, ldx, wpack_tc, R, S, pad, scale, shift, resid, ldr, act, slope, y,
+                            Cout_p, ldy, stream);
+    if (rc == -2 && t_hct) {   // no shared-memory plan with the S-fold weight slots: the plain schedule
+        t_hct = 0;
+        rc = halo_conv_impl(x, N, Hin, Win, Cin_p, ldx, wpack_tc, R, S, pad, scale, shift, resid, ldr, act, slope, y,
+                            Cout_p, ldy, stream);
+    }
+    t_hct = 0;
+    return rc;
 }
 
 MK_EXPORT int mk_conv2d_tc_halo_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc,

@@ -59,15 +59,6 @@ __global__ void __launch_bounds__(256) k_kp_head_fwd(const float* __restrict__ l
     }
 }
 
-MK_EXPORT int mk_kp_head_fwd(const float* logits, int N, int H, int W, int K, int ld, float inv_temperature,
-                             int var_mode, float clip, float* mean, float* var, float* aux, void* stream) {
-    MK_REQUIRE(var_mode == 0 || var_mode == 1, "mk_kp_head_fwd: var_mode");
-    if (N * K == 0) return 0;
-    k_kp_head_fwd<<<N * K, 256, 0, (cudaStream_t)stream>>>(logits, H, W, K, ld, inv_temperature, var_mode, clip, mean,
-                                                           var, aux);
-    return mk_check_launch("mk_kp_head_fwd");
-}
-
 __global__ void __launch_bounds__(256) k_kp_head_bwd(const float* __restrict__ logits, int H, int W, int K, int ld,
                                                      float invT, int var_mode, float clip,
                                                      const float* __restrict__ mean, const float* __restrict__ aux,
@@ -132,11 +123,356 @@ __global__ void __launch_bounds__(256) k_kp_head_bwd(const float* __restrict__ l
     }
 }
 
-MK_EXPORT int mk_kp_head_bwd(const float* logits, int N, int H, int W, int K, int ld, float inv_temperature,
-                             int var_mode, float clip, const float* mean, const float* aux, const float* dmean,
-                             const float* dvar, float* dlogits, void* stream) {
+// ------------------------------------------------------------------------------------------------ chunked keypoint head
+// The one-block-per-(frame, keypoint) kernels above read their channel with a 4-byte load every `ld` floats and run
+// N*K blocks: at 256x256 x 16 frames x 10 keypoints that is 160 blocks x 3 dependent passes = 410 us (fwd) + 390 us
+// (bwd) for 50 MB of logits.  The chunked kernels give one block a CHUNK of pixels and ALL channels of them (float4
+// loads of whole pixels: coalesced, every byte used), N x C blocks; the softmax statistics are combined across chunks
+// from per-chunk partials in a fixed order (deterministic, no float atomics).  `scratch` holds the partials.
+//   fwd 1: per chunk  local max m_c, se_c = sum e^{v - m_c}, sx_c, sy_c            -> part1[n][c][k][4], gsum[n][c][2]
+//   fwd 2: combine -> m, se, mean; per chunk covariance partials                      -> part2[n][c][k][3];
+//          the LAST block of a frame (atomic counter) adds them up and writes mean / var / aux
+//   bwd 1: per chunk  s_c = sum p * dp                                                 -> part1[n][c][k][0]
+//   bwd 2: combine s; dlogits = invT * p * (dp - s) for the chunk, pad channels zeroed (no memset)
+constexpr int KPH_THREADS = 256;
+constexpr int KPH_MAXC = 64;
+
+static inline int kph_chunks(int hw) {
+    int c = hw / 1024;
+    if (c < 1) c = 1;
+    if (c > KPH_MAXC) c = KPH_MAXC;
+    return c;
+}
+// floats of `scratch` for mk_kp_head_fwd / mk_kp_head_bwd
+MK_EXPORT int mk_kp_head_scratch_floats(int N, int H, int W, int K, long long* out) {
+    MK_REQUIRE(out != nullptr, "mk_kp_head_scratch_floats: out is NULL");
+    const int C = kph_chunks(H * W);
+    const int K4 = (K + 3) & ~3;
+    *out = (long long)N * ((long long)C * (7 * K4 + 4) + 4);
+    return 0;
+}
+
+struct KphP {
+    const float* logits; int H, W, K, ld, C, chunk; float invT; int var_mode; float clip;
+    float* part1; float* gsum; float* part2; unsigned* counter;   // views into scratch
+};
+
+__device__ __forceinline__ float f4get(const float4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+
+// block-wide reduction of NV per-thread values into red_out[NV] (shared), sum or max
+template <int NV, bool MAX>
+__device__ __forceinline__ void kph_reduce(float (&v)[NV], float* red /* NV * 8 */, float* out /* NV */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = MAX ? warp_max(v[i]) : warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) red[i * 8 + wid] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        float t = red[threadIdx.x * 8];
+#pragma unroll
+        for (int w = 1; w < KPH_THREADS / 32; ++w) t = MAX ? fmaxf(t, red[threadIdx.x * 8 + w]) : t + red[threadIdx.x * 8 + w];
+        out[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
+template <int KV>
+__global__ void __launch_bounds__(KPH_THREADS) k_kph_fwd1(const KphP p) {
+    constexpr int K4 = 4 * KV;
+    __shared__ float red[(3 * K4 + 2) * 8];
+    __shared__ float bm[K4];
+    __shared__ float outv[3 * K4 + 2];
+    const int n = blockIdx.y, c = blockIdx.x;
+    const int hw = p.H * p.W;
+    const int i0 = c * p.chunk, i1 = min(hw, i0 + p.chunk);
+    const float* base = p.logits + (long long)n * hw * p.ld;
+    if (c == 0 && threadIdx.x == 0) p.counter[n] = 0u;
+    float m[K4];
+#pragma unroll
+    for (int j = 0; j < K4; ++j) m[j] = -INFINITY;
+    for (int i = i0 + threadIdx.x; i < i1; i += KPH_THREADS) {
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            const float4 v = ldg4(base + (long long)i * p.ld + 4 * q);
+            m[4 * q] = fmaxf(m[4 * q], v.x * p.invT); m[4 * q + 1] = fmaxf(m[4 * q + 1], v.y * p.invT);
+            m[4 * q + 2] = fmaxf(m[4 * q + 2], v.z * p.invT); m[4 * q + 3] = fmaxf(m[4 * q + 3], v.w * p.invT);
+        }
+    }
+    kph_reduce<K4, true>(m, red, bm);
+    float acc[3 * K4 + 2];
+#pragma unroll
+    for (int j = 0; j < 3 * K4 + 2; ++j) acc[j] = 0.f;
+    for (int i = i0 + threadIdx.x; i < i1; i += KPH_THREADS) {
+        const float gx = grid_coord(i % p.W, p.W), gy = grid_coord(i / p.W, p.H);
+        acc[3 * K4] += gx; acc[3 * K4 + 1] += gy;
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            const float4 v = ldg4(base + (long long)i * p.ld + 4 * q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float e = expf(f4get(v, j) * p.invT - bm[4 * q + j]);
+                acc[4 * q + j] += e; acc[K4 + 4 * q + j] += e * gx; acc[2 * K4 + 4 * q + j] += e * gy;
+            }
+        }
+    }
+    kph_reduce<3 * K4 + 2, false>(acc, red, outv);
+    if (threadIdx.x < K4) {
+        float* o = p.part1 + (((long long)n * p.C + c) * K4 + threadIdx.x) * 4;
+        o[0] = bm[threadIdx.x]; o[1] = outv[threadIdx.x]; o[2] = outv[K4 + threadIdx.x]; o[3] = outv[2 * K4 + threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+        p.gsum[((long long)n * p.C + c) * 2] = outv[3 * K4];
+        p.gsum[((long long)n * p.C + c) * 2 + 1] = outv[3 * K4 + 1];
+    }
+}
+
+template <int KV>
+__global__ void __launch_bounds__(KPH_THREADS) k_kph_fwd2(const KphP p, float* __restrict__ mean, float* __restrict__ var,
+                                                          float* __restrict__ aux) {
+    constexpr int K4 = 4 * KV;
+    __shared__ float red[3 * K4 * 8];
+    __shared__ float sm[K4], sse[K4], smx[K4], smy[K4];
+    __shared__ float outv[3 * K4];
+    __shared__ int last;
+    const int n = blockIdx.y, c = blockIdx.x;
+    const int hw = p.H * p.W;
+    if (threadIdx.x < K4) {   // combine the chunk partials of this frame (fixed order)
+        const int k = threadIdx.x;
+        const float* pp = p.part1 + ((long long)n * p.C * K4 + k) * 4;
+        float M = -INFINITY;
+        for (int cc = 0; cc < p.C; ++cc) M = fmaxf(M, pp[(long long)cc * K4 * 4]);
+        float se = 0.f, sx = 0.f, sy = 0.f, gx = 0.f, gy = 0.f;
+        for (int cc = 0; cc < p.C; ++cc) {
+            const float* q = pp + (long long)cc * K4 * 4;
+            const float f = expf(q[0] - M);
+            se += q[1] * f; sx += q[2] * f; sy += q[3] * f;
+            gx += p.gsum[((long long)n * p.C + cc) * 2]; gy += p.gsum[((long long)n * p.C + cc) * 2 + 1];
+        }
+        sm[k] = M; sse[k] = se;
+        smx[k] = sx / se + 1e-7f * gx;
+        smy[k] = sy / se + 1e-7f * gy;
+    }
+    __syncthreads();
+    const int i0 = c * p.chunk, i1 = min(hw, i0 + p.chunk);
+    const float* base = p.logits + (long long)n * hw * p.ld;
+    float acc[3 * K4];
+#pragma unroll
+    for (int j = 0; j < 3 * K4; ++j) acc[j] = 0.f;
+    for (int i = i0 + threadIdx.x; i < i1; i += KPH_THREADS) {
+        const float gx = grid_coord(i % p.W, p.W), gy = grid_coord(i / p.W, p.H);
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            const float4 v = ldg4(base + (long long)i * p.ld + 4 * q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * q + j;
+                const float pr = expf(f4get(v, j) * p.invT - sm[k]) / sse[k] + 1e-7f;
+                const float dx = gx - smx[k], dy = gy - smy[k];
+                acc[k] += pr * dx * dx; acc[K4 + k] += pr * dx * dy; acc[2 * K4 + k] += pr * dy * dy;
+            }
+        }
+    }
+    kph_reduce<3 * K4, false>(acc, red, outv);
+    if (threadIdx.x < K4) {
+        float* o = p.part2 + (((long long)n * p.C + c) * K4 + threadIdx.x) * 3;
+        o[0] = outv[threadIdx.x]; o[1] = outv[K4 + threadIdx.x]; o[2] = outv[2 * K4 + threadIdx.x];
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(p.counter + n, 1u) == (unsigned)(p.C - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < p.K) {   // the last block of the frame: covariance totals, clip, outputs
+        const int k = threadIdx.x;
+        float a = 0.f, b = 0.f, d = 0.f;
+        for (int cc = 0; cc < p.C; ++cc) {
+            const volatile float* q = p.part2 + (((long long)n * p.C + cc) * K4 + k) * 3;
+            a += q[0]; b += q[1]; d += q[2];
+        }
+        float cq = b;
+        const long long o = (long long)n * p.K + k;
+        mean[o * 2] = smx[k];
+        mean[o * 2 + 1] = smy[k];
+        float* ax = aux + o * 8;
+        ax[0] = sm[k]; ax[1] = sse[k]; ax[2] = a; ax[3] = b; ax[4] = cq; ax[5] = d; ax[6] = 0.f; ax[7] = 0.f;
+        if (p.var_mode == 0) {
+            if (p.clip > 0.f) {
+                const float s1 = a * a + b * b + cq * cq + d * d;
+                const float u = a * a + b * b - cq * cq - d * d, vv = a * cq + b * d;
+                const float s2 = sqrtf(u * u + 4.f * vv * vv);
+                const float sg = sqrtf((s1 - s2) / 2.f);
+                const float f = fmaxf(p.clip, sg);
+                a = f * a / sg; b = f * b / sg; cq = f * cq / sg; d = f * d / sg;
+                ax[6] = sg;
+            }
+            var[o * 4] = a; var[o * 4 + 1] = b; var[o * 4 + 2] = cq; var[o * 4 + 3] = d;
+        } else {
+            var[o] = (a + d) * 0.5f;
+        }
+    }
+}
+
+// per-channel constants of the backward pass (same algebra as k_kp_head_bwd), threads k < K
+struct KphB { float m, se, mx, my, amx, amy, g00, gxy, g11; };
+__device__ __forceinline__ KphB kph_bwd_consts(int hw, int K, int var_mode, float clip, long long o, const float* mean,
+                                               const float* aux, const float* dmean, const float* dvar) {
+    KphB r;
+    const float* ax = aux + o * 8;
+    r.m = ax[0]; r.se = ax[1];
+    const float a = ax[2], b = ax[3], c = ax[4], d = ax[5];
+    r.mx = mean[o * 2]; r.my = mean[o * 2 + 1];
+    float g00, g01, g10, g11;
+    if (var_mode == 0) {
+        g00 = dvar[o * 4]; g01 = dvar[o * 4 + 1]; g10 = dvar[o * 4 + 2]; g11 = dvar[o * 4 + 3];
+        if (clip > 0.f) {
+            const float sg = ax[6];
+            if (sg < clip) {
+                const float f = clip / sg;
+                const float inner = g00 * a + g01 * b + g10 * c + g11 * d;
+                const float dsg = -clip / (sg * sg) * inner;
+                const float u = a * a + b * b - c * c - d * d, vv = a * c + b * d;
+                const float s2 = sqrtf(u * u + 4.f * vv * vv);
+                const float ds1 = dsg / (4.f * sg), ds2 = -dsg / (4.f * sg);
+                const float du = s2 > 0.f ? ds2 * u / s2 : 0.f, dv = s2 > 0.f ? ds2 * 4.f * vv / s2 : 0.f;
+                g00 = f * g00 + ds1 * 2.f * a + du * 2.f * a + dv * c;
+                g01 = f * g01 + ds1 * 2.f * b + du * 2.f * b + dv * d;
+                g10 = f * g10 + ds1 * 2.f * c - du * 2.f * c + dv * a;
+                g11 = f * g11 + ds1 * 2.f * d - du * 2.f * d + dv * b;
+            }
+        }
+    } else {
+        g00 = g11 = dvar[o] * 0.5f;
+        g01 = g10 = 0.f;
+    }
+    r.g00 = g00; r.g11 = g11; r.gxy = g01 + g10;
+    const float leak = (float)hw * 1e-7f;
+    r.amx = dmean[o * 2] + (2.f * g00 * r.mx + r.gxy * r.my) * leak;
+    r.amy = dmean[o * 2 + 1] + (r.gxy * r.mx + 2.f * g11 * r.my) * leak;
+    return r;
+}
+
+template <int KV, int PHASE>
+__global__ void __launch_bounds__(KPH_THREADS) k_kph_bwd(const KphP p, const float* __restrict__ mean,
+                                                         const float* __restrict__ aux, const float* __restrict__ dmean,
+                                                         const float* __restrict__ dvar, float* __restrict__ dlogits) {
+    constexpr int K4 = 4 * KV;
+    __shared__ float red[K4 * 8];
+    __shared__ KphB cb[K4];
+    __shared__ float stot[K4];
+    const int n = blockIdx.y, c = blockIdx.x;
+    const int hw = p.H * p.W;
+    if (threadIdx.x < K4) {
+        if (threadIdx.x < p.K) {
+            cb[threadIdx.x] = kph_bwd_consts(hw, p.K, p.var_mode, p.clip, (long long)n * p.K + threadIdx.x, mean, aux, dmean, dvar);
+        } else {   // pad channels: p = exp(0 - 0) / 1, dp = 0 -> gradient 0
+            KphB z = {0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            cb[threadIdx.x] = z;
+        }
+        if (PHASE == 2) {
+            float t = 0.f;
+            for (int cc = 0; cc < p.C; ++cc) t += p.part1[((long long)n * p.C + cc) * K4 + threadIdx.x];
+            stot[threadIdx.x] = t;
+        }
+    }
+    __syncthreads();
+    const int i0 = c * p.chunk, i1 = min(hw, i0 + p.chunk);
+    const float* base = p.logits + (long long)n * hw * p.ld;
+    float acc[K4];
+#pragma unroll
+    for (int j = 0; j < K4; ++j) acc[j] = 0.f;
+    for (int i = i0 + threadIdx.x; i < i1; i += KPH_THREADS) {
+        const float gx = grid_coord(i % p.W, p.W), gy = grid_coord(i / p.W, p.H);
+#pragma unroll
+        for (int q = 0; q < KV; ++q) {
+            const float4 v = ldg4(base + (long long)i * p.ld + 4 * q);
+            float o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const KphB& k = cb[4 * q + j];
+                const float pr = expf(f4get(v, j) * p.invT - k.m) / k.se;
+                const float dx = gx - k.mx, dy = gy - k.my;
+                const float dp = gx * k.amx + gy * k.amy + k.g00 * dx * dx + k.gxy * dx * dy + k.g11 * dy * dy;
+                if (PHASE == 1) acc[4 * q + j] += pr * dp;
+                else o4[j] = (4 * q + j < p.K) ? p.invT * pr * (dp - stot[4 * q + j]) : 0.f;
+            }
+            if (PHASE == 2) st4(dlogits + ((long long)n * hw + i) * p.ld + 4 * q, make_float4(o4[0], o4[1], o4[2], o4[3]));
+        }
+        if (PHASE == 2) {
+            for (int q = KV; 4 * q < p.ld; ++q)   // (ld > K4 never happens with ld = pad4(K); kept for safety)
+                st4(dlogits + ((long long)n * hw + i) * p.ld + 4 * q, f4zero());
+        }
+    }
+    if (PHASE == 1) {
+        __shared__ float outv[K4];
+        kph_reduce<K4, false>(acc, red, outv);
+        if (threadIdx.x < K4) p.part1[((long long)n * p.C + c) * K4 + threadIdx.x] = outv[threadIdx.x];
+    }
+}
+
+static void kph_fill(KphP& p, const float* logits, int N, int H, int W, int K, int ld, float invT, int var_mode,
+                     float clip, float* scratch) {
+    const int K4 = (K + 3) & ~3;
+    p.logits = logits; p.H = H; p.W = W; p.K = K; p.ld = ld; p.invT = invT; p.var_mode = var_mode; p.clip = clip;
+    p.C = kph_chunks(H * W);
+    p.chunk = (H * W + p.C - 1) / p.C;
+    p.part1 = scratch;
+    p.part2 = p.part1 + (long long)N * p.C * K4 * 4;
+    p.gsum = p.part2 + (long long)N * p.C * K4 * 3;
+    p.counter = reinterpret_cast<unsigned*>(p.gsum + (long long)N * p.C * 2);
+}
+
+MK_EXPORT int mk_kp_head_fwd(const float* logits, int N, int H, int W, int K, int ld, float inv_temperature,
+                             int var_mode, float clip, float* mean, float* var, float* aux, float* scratch,
+                             void* stream) {
+    MK_REQUIRE(var_mode == 0 || var_mode == 1, "mk_kp_head_fwd: var_mode");
     if (N * K == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    const int K4 = (K + 3) & ~3;
+    if (scratch && ld == K4 && K4 <= 16 && N <= 65535) {
+        KphP p;
+        kph_fill(p, logits, N, H, W, K, ld, inv_temperature, var_mode, clip, scratch);
+        dim3 grid((unsigned)p.C, (unsigned)N);
+        switch (K4 / 4) {
+            case 1: k_kph_fwd1<1><<<grid, KPH_THREADS, 0, st>>>(p); k_kph_fwd2<1><<<grid, KPH_THREADS, 0, st>>>(p, mean, var, aux); break;
+            case 2: k_kph_fwd1<2><<<grid, KPH_THREADS, 0, st>>>(p); k_kph_fwd2<2><<<grid, KPH_THREADS, 0, st>>>(p, mean, var, aux); break;
+            case 3: k_kph_fwd1<3><<<grid, KPH_THREADS, 0, st>>>(p); k_kph_fwd2<3><<<grid, KPH_THREADS, 0, st>>>(p, mean, var, aux); break;
+            default: k_kph_fwd1<4><<<grid, KPH_THREADS, 0, st>>>(p); k_kph_fwd2<4><<<grid, KPH_THREADS, 0, st>>>(p, mean, var, aux); break;
+        }
+        return mk_check_launch("mk_kp_head_fwd(chunked)");
+    }
+    k_kp_head_fwd<<<N * K, 256, 0, st>>>(logits, H, W, K, ld, inv_temperature, var_mode, clip, mean, var, aux);
+    return mk_check_launch("mk_kp_head_fwd");
+}
+
+MK_EXPORT int mk_kp_head_bwd(const float* logits, int N, int H, int W, int K, int ld, float inv_temperature,
+                             int var_mode, float clip, const float* mean, const float* aux, const float* dmean,
+                             const float* dvar, float* dlogits, float* scratch, void* stream) {
+    if (N * K == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K4 = (K + 3) & ~3;
+    if (scratch && ld == K4 && K4 <= 16 && N <= 65535) {
+        KphP p;
+        kph_fill(p, logits, N, H, W, K, ld, inv_temperature, var_mode, clip, scratch);
+        dim3 grid((unsigned)p.C, (unsigned)N);
+#define KPH_BWD(KV)                                                                                              \
+    do {                                                                                                         \
+        k_kph_bwd<KV, 1><<<grid, KPH_THREADS, 0, st>>>(p, mean, aux, dmean, dvar, dlogits);                      \
+        k_kph_bwd<KV, 2><<<grid, KPH_THREADS, 0, st>>>(p, mean, aux, dmean, dvar, dlogits);                      \
+    } while (0)
+        switch (K4 / 4) {
+            case 1: KPH_BWD(1); break;
+            case 2: KPH_BWD(2); break;
+            case 3: KPH_BWD(3); break;
+            default: KPH_BWD(4); break;
+        }
+#undef KPH_BWD
+        return mk_check_launch("mk_kp_head_bwd(chunked)");
+    }
     if (ld != K) {
         cudaError_t e = cudaMemsetAsync(dlogits, 0, sizeof(float) * (size_t)N * H * W * ld, st);
         if (e != cudaSuccess) { mk_set_error("mk_kp_head_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
@@ -323,8 +659,10 @@ MK_EXPORT int mk_movement_embed_fwd(const float* src, int lds, int C, const floa
     return mk_check_launch("mk_movement_embed_fwd");
 }
 
-// backward: one block per (frame n, keypoint k); 14 block-reduced sums, closed-form chain in thread 0.
-__global__ void __launch_bounds__(256) k_movement_embed_bwd(const EmbP p, const float* __restrict__ dout, int ldo,
+// backward: one block per (frame n, keypoint k); 14 block-reduced sums, closed-form chain in thread 0.  1024 threads:
+// the B*d*K blocks (80 at taichi@256) leave half the SMs idle and each walks h*w strided pixels - the block size is the
+// only parallelism this kernel has (256 threads: 225 us per launch at 256x256).
+__global__ void __launch_bounds__(1024) k_movement_embed_bwd(const EmbP p, const float* __restrict__ dout, int ldo,
                                                             float* __restrict__ d_kd_mean, float* __restrict__ d_kd_var,
                                                             float* __restrict__ d_ks_mean,
                                                             float* __restrict__ d_ks_var) {
@@ -445,7 +783,7 @@ MK_EXPORT int mk_movement_embed_bwd(const float* src, int lds, int C, const floa
                        norm_const, heat_sums);
     if (rc) return rc;
     if (B * d * K == 0) return 0;
-    k_movement_embed_bwd<<<B * d * K, 256, 0, (cudaStream_t)stream>>>(p, dout, ldo, d_kd_mean, d_kd_var, d_ks_mean,
+    k_movement_embed_bwd<<<B * d * K, 1024, 0, (cudaStream_t)stream>>>(p, dout, ldo, d_kd_mean, d_kd_var, d_ks_mean,
                                                                       d_ks_var);
     return mk_check_launch("mk_movement_embed_bwd");
 }

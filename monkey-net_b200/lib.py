@@ -96,5 +96,13 @@ def call_soft(name, soft, *args):
     raise MonkeyLibError('%s failed (%d): %s' % (name, rc, lib.mk_last_error().decode()))
 
 
+def query(name, *args):
+    """host-side entry points that launch nothing (planner dry runs, size queries): not counted as kernel launches"""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise MonkeyLibError('%s failed (%d): %s' % (name, rc, lib.mk_last_error().decode()))
+
+
 def launches():
     return _Counter.n

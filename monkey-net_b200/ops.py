@@ -756,6 +756,15 @@ def resize(a, h, w, mode):
 
 
 # ====================================================================================================== keypoints
+def _kp_scratch(N, H, W, K, like):
+    """chunk partials of the many-block keypoint-head kernels (size asked from the library; a host-side query, not a
+    launch)"""
+    import ctypes
+    n = ctypes.c_longlong(0)
+    lib.query('mk_kp_head_scratch_floats', N, H, W, K, ctypes.byref(n))
+    return _empty(int(n.value), like=like)
+
+
 class _KPHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, B, D, K, inv_t, var_mode, clip):
@@ -765,7 +774,7 @@ class _KPHead(torch.autograd.Function):
         var = _empty(B, D, K, 2, 2, like=logits) if var_mode == 0 else _empty(B, D, K, 1, 1, like=logits)
         aux = _empty(N, K, 8, like=logits)
         lib.call('mk_kp_head_fwd', logits.data_ptr(), N, H, W, K, ld, inv_t, var_mode, clip, mean.data_ptr(),
-                 var.data_ptr(), aux.data_ptr(), _stream())
+                 var.data_ptr(), aux.data_ptr(), _kp_scratch(N, H, W, K, logits).data_ptr(), _stream())
         ctx.meta = (K, inv_t, var_mode, clip)
         ctx.save_for_backward(logits, mean, aux)
         return mean, var
@@ -782,7 +791,8 @@ class _KPHead(torch.autograd.Function):
             dvar = _zeros(N * K * (4 if var_mode == 0 else 1), like=logits)
         dl = _empty(N, H, W, ld, like=logits)
         lib.call('mk_kp_head_bwd', logits.data_ptr(), N, H, W, K, ld, inv_t, var_mode, clip, mean.data_ptr(),
-                 aux.data_ptr(), dmean.data_ptr(), dvar.data_ptr(), dl.data_ptr(), _stream())
+                 aux.data_ptr(), dmean.data_ptr(), dvar.data_ptr(), dl.data_ptr(),
+                 _kp_scratch(N, H, W, K, logits).data_ptr(), _stream())
         return dl, None, None, None, None, None, None
 
 

@@ -274,7 +274,10 @@ def test_resize(mode, h0, h):
 
 # ------------------------------------------------------------------------------------------------------ keypoints
 @pytest.mark.parametrize('K,H,kp_variance,clip', [(10, 16, 'matrix', None), (4, 32, 'matrix', 0.5),
-                                                   (10, 16, 'matrix', 0.001), (5, 16, 'single', None)])
+                                                   (10, 16, 'matrix', 0.001), (5, 16, 'single', None),
+                                                   # several pixel chunks per frame (chunked many-block kernels):
+                                                   (10, 64, 'matrix', 0.001), (7, 50, 'matrix', None),
+                                                   (3, 64, 'single', None), (13, 48, 'matrix', 0.5)])
 def test_kp_head(K, H, kp_variance, clip):
     o, mo = ops(), oracle()
     torch.manual_seed(K + H)

@@ -103,7 +103,7 @@ def test_every_layer_has_a_valid_tensor_core_plan(name, res, batch):
                         assert not ct or (rb == 1 and k_ > 1 and co_ % 16 == 0 and npad == k_ * co_ <= 256)
                         nslots = (k_ if ct else k_ * k_) * ((ci_ + 31) // 32)
                         assert (resident and b_sl == nslots <= 40) or (not resident and 2 <= b_sl <= 8)
-                        assert gx * gy <= 148 and ntiles >= gx and (fl & 1) == x3 and ((fl >> 1) & 3) in (1, 2)
+                        assert gx * gy <= 148 and ntiles >= gx and (fl & 1) == x3 and ((fl >> 1) & 3) in (1, 2, 3)
                         nstg = (fl >> 1) & 3
                         assert a_st * a_stage + b_sl * b_slot + nstg * (1 + res_) * twv * 8 * 128 + 2048 == smem
                 rc, o = plan(lib, 'mk_conv2d_wgrad_halo_plan', N, H, W, cin_p, cop, k, k, pad, x3)
