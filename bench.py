@@ -19,7 +19,7 @@ Prints ONE JSON line (rank 0).  `value` = whole-job frames/s with inputs residen
 the public API with pinned HOST inputs, H2D copy and D2H loss read inside the timed region; `roofline` = the
 convolution kernels' algorithmic FLOP/s vs the measured tensor peak; `cpu_baseline` = the reference's modules (from
 the byte-compiled oracle/_ref build; the oracle port when that is absent) timed on this box's host cores on a bounded
-sample of the same workload.  Training convolutions run in the 'auto' arithmetic: 3xTF32 tensor-core kernels
+sample of the same workload.  Training convolutions run in the 'auto' arithmetic: split-operand (TF32 + BF16 cross terms) tensor-core kernels
 (fp32-accurate); `tf32_fast` reports the same step with 1xTF32 for readers who train at TF32 like stock PyTorch.
 """
 import argparse
@@ -307,17 +307,17 @@ def roofline(m, flops, pk, steps_note=''):
     x3 = m['conv_mode'] in ('auto', 'tf32x3')
     return {'bound': 'tensor',
             'kernel': 'implicit-GEMM convolutions, fwd + dgrad + wgrad: k_conv_halo / k_conv_tc / k_wgrad_tc (tcgen05 '
-                      'kind::tf32, %s)' % ('3xTF32 = three MMAs per product' if x3 else '1xTF32'),
+                      'kind::tf32%s)' % (' + one kind::f16 BF16 MMA for the cross terms = 2 MMAs per product' if x3 else ', 1xTF32'),
             'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
             'frac': achieved / pk['bf16_tflops_sustained'],
             'traffic': traffic,
             'frac_of_tf32_peak': achieved / (pk['bf16_tflops_sustained'] / 2),
-            'frac_of_3xtf32_ceiling': achieved / (pk['bf16_tflops_sustained'] / 6) if x3 else None,
+            'frac_of_reference_precision_ceiling': achieved / (pk['bf16_tflops_sustained'] / 4) if x3 else None,
             'note': 'achieved = ALGORITHMIC conv FLOPs of the step (3*KP2 + 3*G + 12*D, 2*MACs of the reference convs) / '
                     'summed device time of the conv launches (CUDA events around every launch, eager pass, stream parked '
-                    'so launches are back to back).  kind::tf32 issues at half the bf16 rate and the 3xTF32 mode spends '
-                    'three MMAs per product, so the reference-precision ceiling is peak/6; `frac` stays against the '
-                    'measured bf16 peak as the contract asks.',
+                    'so launches are back to back).  kind::tf32 issues at half the bf16 rate; the reference-precision mode adds '
+                    'one BF16 MMA (K = 16, same duration) for the two cross terms, so its ceiling is peak/4 (3xTF32 until '
+                    'visit 16: peak/6); `frac` stays against the measured bf16 peak as the contract asks.',
             'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
             'launches_per_step': m['conv_launches_per_step'], 'conv_ms_per_step': m['conv_ms_per_step'],
             'conv_share_of_step': m['conv_ms_per_step'] / m['ms_per_step']}
@@ -343,8 +343,8 @@ def run_ours(args):
         'metric': METRIC, 'value': main['value'], 'unit': 'frames/s', 'n_gpus': h.world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None,
-        'dtype': {'auto': 'f32 (3xTF32 tensor-core convolutions: fp32-accurate products, fp32 accumulate; fp32 elsewhere)',
-                  'tf32x3': 'f32 (3xTF32 tensor-core convolutions)', 'tf32': 'tf32 tensor-core convs (fp32 accumulate)',
+        'dtype': {'auto': 'f32 (split-operand tensor-core convolutions: TF32 main term + BF16 cross terms = fp32-accurate products, fp32 accumulate; fp32 elsewhere)',
+                  'tf32x3': 'f32 (split-operand tensor-core convolutions: TF32 main term + BF16 cross terms)', 'tf32': 'tf32 tensor-core convs (fp32 accumulate)',
                   'fp32': 'f32 (FFMA convolutions)'}[mode],
         'data': 'synthetic (torch.rand frames, seeded default-init weights)',
         'config': {'workload': 'config/%s.yaml nets @%dx%d, training step (train.py:110-136: G fwd+bwd+Adam(G,KP), D '
@@ -746,7 +746,7 @@ def run_transfer(args):
         out = {'metric': r['metric'], 'value': frames / (float(t[0]) / 1e3), 'unit': 'frames/s', 'n_gpus': world,
                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(t[0]), 'higher_is_better': True,
                'scaling': 'weak', 'vs_baseline': None,
-               'dtype': 'geometry networks 3xTF32, appearance path 1xTF32 tensor-core convs (fp32 accumulate)',
+               'dtype': 'geometry networks fp32-accurate (TF32 + BF16 cross terms), appearance path 1xTF32 tensor-core convs (fp32 accumulate)',
                'data': 'synthetic (torch.rand frames, seeded default-init weights)',
                'config': {'workload': r['workload'], 'parallelism': 'replicas x%d' % world,
                           'l2': 'flushed between timed calls'},

@@ -62,6 +62,7 @@ constexpr int HK = 32;                 // fp32 channels per chunk = 128 bytes
 constexpr int MAXA = 4, MAXB = 40;     // ring depth bounds (MAXB also bounds the resident slots: 9 taps x 4 chunks = 36)
 constexpr int H_SMEM_MAX = 227 * 1024;
 constexpr int H_THREADS = 384;
+constexpr int H_FIXED = 3072;   // barriers (<= 848 B) + the CTA's scale / shift vectors (1 KB) + 1023 B alignment slack
 
 struct HP {
     int N, Ho, Wo, Cout_p, Cin_p, R, S, pad;
@@ -181,6 +182,8 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* r_full = tmem_empty + 2;
     uint64_t* r_empty = r_full + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + 4);
+    float* s_scale = reinterpret_cast<float*>(tmem_slot + 4);   // this CTA's 128 output channels: epilogue affine
+    float* s_shift = s_scale + 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cout0 = blockIdx.y * 128;
@@ -202,6 +205,11 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
         for (int i = 0; i < 4; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 128) {   // the epilogue reads these 8 x float4 per group from shared memory (broadcast), not from L1/L2
+        const int co = cout0 + (int)threadIdx.x;
+        s_scale[threadIdx.x] = (p.scale && co < p.Cout_p) ? p.scale[co] : 1.f;
+        s_shift[threadIdx.x] = (p.shift && co < p.Cout_p) ? p.shift[co] : 0.f;
     }
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -430,13 +438,14 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (valid) {
                         const float4* rrow = reinterpret_cast<const float4*>(rbuf + sb * p.stg_bytes + srow * 128);
                         float4* orow = reinterpret_cast<float4*>(sbuf + srow * 128);
+                        const float4* ssc = reinterpret_cast<const float4*>(s_scale + cbase);
+                        const float4* ssh = reinterpret_cast<const float4*>(s_shift + cbase);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (4 * j >= cn) break;
-                            const int co = cout0 + cbase + 4 * j;
+                            if (4 * j >= cn) continue;
                             float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            if (p.scale) o = o * ldg4(p.scale + co);
-                            if (p.shift) o = o + ldg4(p.shift + co);
+                            if (p.scale) o = o * ssc[j];
+                            if (p.shift) o = o + ssh[j];
                             if (p.has_resid) o = o + rrow[j ^ sw];
                             if (p.act == 1) {
                                 o.x = o.x > 0.f ? o.x : o.x * p.slope; o.y = o.y > 0.f ? o.y : o.y * p.slope;
@@ -562,12 +571,12 @@ static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, in
         }
         // resident weights with as many staging buffers as fit (3: every TMA store has two group times to drain)...
         for (int ns = max_nstg; ns >= 1 && !nstg; --ns) {
-            const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + 2048;
+            const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + H_FIXED;
             if (nB <= MAXB && nB * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) { nstg = ns; res = 1; bslots = nB; }
         }
         // ...else a weight ring, where shared memory buys ring depth before a third staging buffer
         for (int ns = max_nstg < 2 ? max_nstg : 2; ns >= 1 && !nstg; --ns) {
-            const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + 2048;
+            const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + H_FIXED;
             if ((ns == 1 ? 2 : 3) * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) {
                 nstg = ns; res = 0;
                 bslots = (H_SMEM_MAX - fixed - 2 * a_stage) / p.b_slot;
@@ -617,7 +626,7 @@ static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, in
         mk_set_error("mk_conv2d_tc_halo: %d tiles, %.0f %% useful: left to mk_conv2d_tc", p.ntiles, 100.0 * useful);
         return -2;
     }
-    const int fixed = p.nstg * (1 + p.has_resid) * p.stg_bytes + 2048 /*barriers + alignment*/;
+    const int fixed = p.nstg * (1 + p.has_resid) * p.stg_bytes + H_FIXED;
     int budget = H_SMEM_MAX - fixed;
     if (p.resident) {
         p.b_slots = nB;

@@ -22,7 +22,7 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-# Module-, step- and graph-level suites run in the product's DEFAULT arithmetic ('auto': 3xTF32 tensor-core convs
+# Module-, step- and graph-level suites run in the product's DEFAULT arithmetic ('auto': reference-precision tf32x3 tensor-core convs
 # while autograd records and in the keypoint detector, 1xTF32 for no_grad inference) - the mode bench.py times.
 # Only the op-level suite pins 'fp32': its convolution cases are the tests of the exact FFMA kernels themselves.
 _FP32_MODULES = ('test_gpu_1_ops',)

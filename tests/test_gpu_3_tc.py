@@ -1,4 +1,4 @@
-"""Tensor-core (tcgen05 / TMA) convolution kernels - 1xTF32, 3xTF32 - and the exact FFMA kernels: kernel-level parity
+"""Tensor-core (tcgen05 / TMA) convolution kernels - 1xTF32, reference precision (tf32x3: TF32 main term + BF16 cross terms) - and the exact FFMA kernels: kernel-level parity
 against torch's F.conv2d / autograd in double precision on the same device buffers, and module-level parity of the
 whole generator in the tensor-core modes against the CPU oracle."""
 import pytest
@@ -35,7 +35,7 @@ CASES = [
 
 # Every kernel is compared with torch's own convolution evaluated in DOUBLE precision on the same device buffers
 # (F.conv2d + autograd, the op the reference calls) - not with another kernel of this repository.  Tolerances are
-# relative to the output's max-abs: TF32 keeps 10 mantissa bits (2e-3), 3xTF32 and the FFMA kernel are fp32-accurate.
+# relative to the output's max-abs: TF32 keeps 10 mantissa bits (2e-3), tf32x3 and the FFMA kernel are fp32-accurate.
 KERNEL_TOL = {'tf32': 2e-3, 'tf32x3': 2e-5, 'ffma': 1e-5}
 
 
@@ -193,20 +193,20 @@ def test_train_step_tf32_mode_gradients():
     print('tf32 train step: gradient cosine vs fp32 oracle: median %.5f, 5 worst %s' % (med, coss[:5]))
     # TF32 (10-bit mantissa) through ~25 conv+BN layers and the warp's d(grid).  The fp32 reference algorithm itself
     # turns 5e-4 relative conv-output noise into median-cosine 0.97 / worst 0.90 gradients (tools/noise_sensitivity.py),
-    # so that is the envelope a 1xTF32 implementation can be held to - the reason training defaults to 3xTF32.
+    # so that is the envelope a 1xTF32 implementation can be held to - the reason training defaults to tf32x3.
     assert med > 0.9 and coss[0][0] > 0.7, coss[:5]
 
 
 @pytest.mark.parametrize('name,res,batch', [('tiny', 32, 3), ('shapes', 64, 2)])
 def test_train_step_default_mode_gradient_cosine(name, res, batch):
-    """The product's DEFAULT training arithmetic ('auto' -> 3xTF32 tensor-core convolutions): composed G-step
+    """The product's DEFAULT training arithmetic ('auto' -> tf32x3 tensor-core convolutions): composed G-step
     parameter gradients against the fp32 CPU oracle, cosine per parameter tensor.  Bar: median >= 0.9999 (SURVEY
     8(c)); the tail is bounded by the reference's own conditioning (tools/noise_sensitivity_tiny.py: 1e-6 relative
     noise on the oracle's conv outputs moves single gradients by up to 2e-1)."""
     cfg = helpers.tiny_config() if name == 'tiny' else helpers.load_config(name)
     coss = _grad_cosines(cfg, res, batch, 'auto')
     med, p10 = coss[len(coss) // 2][0], coss[len(coss) // 10][0]
-    print('%s auto (3xTF32) train step: gradient cosine vs fp32 oracle: median %.6f, 10th percentile %.6f, 5 worst %s'
+    print('%s auto (tf32x3) train step: gradient cosine vs fp32 oracle: median %.6f, 10th percentile %.6f, 5 worst %s'
           % (name, med, p10, coss[:5]))
     assert med >= 0.9999 and p10 >= 0.999 and coss[0][0] > 0.9, coss[:5]
 
@@ -226,7 +226,7 @@ def test_conv_tc_rejects_unsupported_shapes_without_touching_output():
 @pytest.mark.parametrize('name,res', [('taichi', 64), ('shapes', 64)])
 def test_generator_tensor_core_modes_against_oracle(name, res, mode):
     """Whole keypoint detector + generator, eval / no_grad, against the fp32 CPU oracle.
-      'auto' (product default, what bench.py times): geometry networks 3xTF32, appearance path 1xTF32 -
+      'auto' (product default, what bench.py times): geometry networks tf32x3, appearance path 1xTF32 -
              keypoints <= 2e-5 AND identical pixel indices (the logger.py:99-100 rule, north-star "bit-exact"),
              frame <= 1e-3 (north-star), deformed frame <= 1e-3;
       'tf32' (everything 1xTF32): frame <= 1e-3, keypoints <= 1e-4 (pixel indices may flip next to a .5 boundary)."""
@@ -277,8 +277,8 @@ HALO_CASES = [
     (128, 32, 3, 1, 64, 64, 8, False, 0),     # 36 resident weight slots
     (36, 12, 3, 1, 64, 64, 16, False, 0),     # hourglass head: Cout_p = 12 (one 16-column accumulator)
     (64, 16, 4, 3, 61, 61, 8, False, 0),      # column taps on N: 4 x 16 = 64 accumulator columns, full correlation
-    (32, 64, 3, 1, 40, 40, 4, False, 2),      # column taps on N: 3 x 64 = 192 columns, two output groups, sigmoid
-    (16, 64, 4, 0, 35, 35, 6, True, 1),       # column taps on N at the limit N = 256, residual
+    (96, 64, 3, 1, 64, 64, 8, False, 2),      # column taps on N: 3 x 64 = 192 columns, two output groups, sigmoid
+    (64, 64, 4, 0, 67, 67, 8, True, 1),       # column taps on N at the limit N = 256, residual
 ]
 
 

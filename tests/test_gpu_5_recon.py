@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 # measured on a B200 (round 2): fp32 |kp| 3.5e-8 |frame| 4.8e-7; tf32 |kp| 2.6e-5 |frame| 3.8e-4.  'auto' is the
-# product default (geometry networks 3xTF32, appearance path 1xTF32): the north-star bars incl. identical pixel indices
+# product default (geometry networks tf32x3, appearance path 1xTF32): the north-star bars incl. identical pixel indices
 @pytest.mark.parametrize('mode,tol_kp,tol_frame', [('fp32', 2e-5, 1e-4), ('auto', 2e-5, 1e-3), ('tf32', 1e-4, 1e-3)])
 def test_reconstruction_of_bundled_shapes_video(mode, tol_kp, tol_frame):
     from monkey_net_b200 import ops, transfer_step
