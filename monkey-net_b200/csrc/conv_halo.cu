@@ -435,26 +435,48 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     } else if (cn > 16) tmem_ld32(tacc + (uint32_t)cbase, v);
                     else tmem_ld16(tacc + (uint32_t)cbase, v);
-                    if (valid) {
-                        const float4* rrow = reinterpret_cast<const float4*>(rbuf + sb * p.stg_bytes + srow * 128);
-                        float4* orow = reinterpret_cast<float4*>(sbuf + srow * 128);
+                    // One uniform branch per PASS over the 32 channels, not per float4: an epilogue warp runs alone on its
+                    // scheduler, so its time is its dependent-issue latency - the former loop (5 uniform branches in each of
+                    // 8 iterations, ~500 instructions per group) took ~2200 clk per group and bounded the N >= 128 layers.
+                    {
                         const float4* ssc = reinterpret_cast<const float4*>(s_scale + cbase);
                         const float4* ssh = reinterpret_cast<const float4*>(s_shift + cbase);
+                        if (p.scale) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (4 * j >= cn) continue;
-                            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            if (p.scale) o = o * ssc[j];
-                            if (p.shift) o = o + ssh[j];
-                            if (p.has_resid) o = o + rrow[j ^ sw];
-                            if (p.act == 1) {
-                                o.x = o.x > 0.f ? o.x : o.x * p.slope; o.y = o.y > 0.f ? o.y : o.y * p.slope;
-                                o.z = o.z > 0.f ? o.z : o.z * p.slope; o.w = o.w > 0.f ? o.w : o.w * p.slope;
-                            } else if (p.act == 2) {
-                                o.x = 1.f / (1.f + expf(-o.x)); o.y = 1.f / (1.f + expf(-o.y));
-                                o.z = 1.f / (1.f + expf(-o.z)); o.w = 1.f / (1.f + expf(-o.w));
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = ssc[j];
+                                v[4 * j] *= t.x; v[4 * j + 1] *= t.y; v[4 * j + 2] *= t.z; v[4 * j + 3] *= t.w;
                             }
-                            orow[j ^ sw] = o;
+                        }
+                        if (p.shift) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = ssh[j];
+                                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                            }
+                        }
+                        if (p.has_resid && valid) {
+                            const float4* rrow = reinterpret_cast<const float4*>(rbuf + sb * p.stg_bytes + srow * 128);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (4 * j < cn) {
+                                    const float4 t = rrow[j ^ sw];
+                                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                                }
+                            }
+                        }
+                        if (p.act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+                        } else if (p.act == 2) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+                        }
+                        if (valid) {
+                            float4* orow = reinterpret_cast<float4*>(sbuf + srow * 128);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (4 * j < cn) orow[j ^ sw] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> TMA store reads
@@ -569,20 +591,24 @@ static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, in
             max_nstg = e ? atoi(e) : 3;
             if (max_nstg < 1 || max_nstg > 3) max_nstg = 3;
         }
-        // resident weights with as many staging buffers as fit (3: every TMA store has two group times to drain)...
-        for (int ns = max_nstg; ns >= 1 && !nstg; --ns) {
+        // preference: resident weights with 3 or 2 staging buffers (3: every TMA store has two group times to drain),
+        // a weight ring with 2 (shared memory buys ring depth before a third staging buffer), then either with one
+        auto try_resident = [&](int ns) {
             const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + H_FIXED;
-            if (nB <= MAXB && nB * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) { nstg = ns; res = 1; bslots = nB; }
-        }
-        // ...else a weight ring, where shared memory buys ring depth before a third staging buffer
-        for (int ns = max_nstg < 2 ? max_nstg : 2; ns >= 1 && !nstg; --ns) {
+            if (!nstg && nB <= MAXB && nB * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) { nstg = ns; res = 1; bslots = nB; }
+        };
+        auto try_ring = [&](int ns) {
             const int fixed = ns * (1 + p.has_resid) * p.stg_bytes + H_FIXED;
-            if ((ns == 1 ? 2 : 3) * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) {
+            if (!nstg && (ns == 1 ? 2 : 3) * p.b_slot + 2 * a_stage + fixed <= H_SMEM_MAX) {
                 nstg = ns; res = 0;
                 bslots = (H_SMEM_MAX - fixed - 2 * a_stage) / p.b_slot;
                 if (bslots > 8) bslots = 8;
             }
-        }
+        };
+        for (int ns = max_nstg; ns >= 2; --ns) try_resident(ns);
+        if (max_nstg >= 2) try_ring(2);
+        try_resident(1);
+        try_ring(1);
         if (!nstg) break;
         const double mma_clk = (double)rb * nslot_chunk * ksteps * (128.0 * p.b_rows / 256.0) * (p.x3 ? 2 : 1);
         const double a_bytes = (double)halo_rows * 16 * Cin_p * 4;
