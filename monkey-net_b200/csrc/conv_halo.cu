@@ -515,9 +515,10 @@ static thread_local int t_hct = 0;   // column-taps-on-N requested for this call
 static thread_local int* t_hplan = nullptr;
 
 // Column taps on N pay when the MMA phase of the plain schedule outweighs the epilogue: CT divides the operand rows
-// read per K step by ~2 (3x3) but reads S accumulator column groups per output group and forces RB = 1.  Constants
-// measured on B200 (profiles/r2_conv_micro_v8_ct_on.txt): UTCHMMA = 18 + 0.35 * (M + N) clk, epilogue ~2600 clk per
-// 32-channel group of a 128-pixel tile.  MONKEY_B200_HALO_CT = 0 never, 2 whenever eligible (experiments).
+// read per K step by ~2 (3x3) but reads S accumulator column groups per output group and forces RB = 1.  Per-tile
+// model with constants measured on B200 (profiles/r2_conv_micro_v8..v11): UTCHMMA = 18 + 0.35 * (M + N) clk, epilogue
+// ~1500 clk per 32-channel group of a 128-pixel tile (+300 per extra column tap in CT mode); the slower of the two
+// phases bounds a tile.  MONKEY_B200_HALO_CT = 0 never, 2 whenever eligible (experiments).
 static bool halo_wants_ct(int R, int S, int Cin_p, int Cout_p, int x3) {
     static int ct_env = -1;
     if (ct_env < 0) {
@@ -526,14 +527,16 @@ static bool halo_wants_ct(int R, int S, int Cin_p, int Cout_p, int x3) {
     }
     if (!ct_env || S <= 1 || Cout_p > 128 || Cout_p % 16 || S * Cout_p > 256) return false;
     if (ct_env == 2) return true;
-    const int ksteps = (Cin_p + 7) / 8;
-    const double mma_plain = (double)R * S * ksteps * (18.0 + 0.35 * (128 + Cout_p)) * (x3 ? 2 : 1);
-    const double epilogue = 2600.0 * ((Cout_p + 31) / 32);
-    return mma_plain > 1.2 * epilogue;
+    const int ksteps = (Cin_p + 7) / 8, groups = (Cout_p + 31) / 32;
+    const double passes = x3 ? 2.0 : 1.0;
+    const double mma_plain = passes * R * S * ksteps * (18.0 + 0.35 * (128 + Cout_p));
+    const double mma_ct = passes * R * ksteps * (18.0 + 0.35 * (128 + S * Cout_p));
+    const double epi_plain = 1500.0 * groups, epi_ct = (1500.0 + 300.0 * (S - 1)) * groups;
+    const double t_plain = mma_plain > epi_plain ? mma_plain : epi_plain;
+    const double t_ct = mma_ct > epi_ct ? mma_ct : epi_ct;
+    return t_ct < 0.95 * t_plain;
 }
 
-// Returns 0 on success, -2 when the shape is outside this kernel's envelope or the launch would leave most SMs idle
-// (callers use mk_conv2d_tc, whose split-K serves the few-tile layers).
 static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc,
                           int R, int S, int pad, const float* scale, const float* shift, const float* resid,
                           int ldr, int act, float slope, float* y, int Cout_p, int ldy, void* stream) {
