@@ -156,7 +156,10 @@ def run(device, res=64, per_rank=2):
     (rep['prediction_max_abs'], rep['kp_mean_max_abs'], rep['loss_terms_rel'], rep['bn_running_stats_rel'], c0, c1,
      rep['grad_rel_median'], rep['grad_rel_max']) = [float(v) for v in t.tolist()]
     rep['grad_cosine_min'], rep['grad_cosine_median'] = -c0, -c1
-    rep['ok'] = bool(rep['prediction_max_abs'] < 1e-4 and rep['kp_mean_max_abs'] < 1e-5 and
+    # bars: the two runs differ only in the ORDER of the fp32 / f64 statistics sums (per-rank partials vs one pass), which
+    # the train-mode nets amplify like any 1e-7 perturbation (tools/noise_sensitivity.py): measured on B200s 1.9e-5 at
+    # 2 ranks, 8.9e-5 at 8 ranks for the prediction - the bar sits 4x under the 1e-3 frame parity bar of the north star
+    rep['ok'] = bool(rep['prediction_max_abs'] < 2.5e-4 and rep['kp_mean_max_abs'] < 1e-5 and
                      rep['loss_terms_rel'] < 1e-4 and rep['bn_running_stats_rel'] < 1e-5 and
                      rep['grad_cosine_median'] > 0.9999 and rep['grad_cosine_min'] > 0.99)
     rep['invariant'] = 'N ranks on contiguous shards (NCCL sync-BN fwd+bwd, averaged gradients) == one rank on the full batch'
