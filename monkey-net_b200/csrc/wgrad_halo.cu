@@ -356,10 +356,9 @@ MK_EXPORT int mk_conv2d_wgrad_halo(const float* x, int N, int Hin, int Win, int 
     const int cols = p.nci * S * p.co_pad;
     p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
     long long groups = (long long)co_tiles * ci_groups;
-    long long splits = mk_cdiv(sms, groups);
-    if (splits > p.ntiles) splits = p.ntiles;
-    if (splits < 1) splits = 1;
-    if (splits > 65535) splits = 65535;
+    // pixel splits: one wave of CTAs (1 CTA per SM); the epilogue of a CTA (atomics of nci x S x co x 96..128 rows)
+    // costs about as much as 6 pixel tiles
+    long long splits = pick_splits(groups, p.ntiles, sms, 6.0, 65535);
     p.tiles_per_split = (int)mk_cdiv(p.ntiles, splits);
     splits = mk_cdiv(p.ntiles, p.tiles_per_split);
     if (p.stages > p.tiles_per_split) p.stages = p.tiles_per_split < 2 ? 2 : p.tiles_per_split;

@@ -273,14 +273,12 @@ MK_EXPORT int mk_conv2d_wgrad_tc(const float* x, int N, int Hin, int Win, int Ci
     // pixel splits: fill the machine (about one CTA per SM - the 512-column case allows no second resident CTA)
     const long long tiles = (long long)co_tiles * p.n_ci_tiles * p.n_tap_groups;
     const int sms = mk_num_sms();
-    long long splits = mk_cdiv((p.tmem_cols <= 256 ? 2LL : 1LL) * sms, tiles);
-    if (splits > p.nchunks) splits = p.nchunks;
-    if (splits < 1) splits = 1;
-    if (splits > 65535) splits = 65535;
+    p.x3 = t_wx3;
+    // (wave-aware: tc_common.cuh:pick_splits; two CTAs share an SM only with <= 256 TMEM columns and 1x slots)
+    long long splits = pick_splits(tiles, p.nchunks, ((p.tmem_cols <= 256 && !p.x3) ? 2LL : 1LL) * sms, 4.0, 65535);
     p.chunks_per_split = (int)mk_cdiv(p.nchunks, splits);
     splits = mk_cdiv(p.nchunks, p.chunks_per_split);
     // rings: never deeper than the loops; within ~100 KB when two CTAs can share an SM, ~200 KB otherwise
-    p.x3 = t_wx3;
     const int budget = (p.tmem_cols <= 256 && tiles * splits > sms && !p.x3) ? 100 * 1024 : 200 * 1024;
     const int a_slot = (p.na_max * BOX_BYTES) << p.x3, b_slot = (p.nb_max * BOX_BYTES) << p.x3;
     p.a_slots = p.chunks_per_split < 2 ? 1 : 2;
