@@ -453,6 +453,45 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
     wp[i] = v;
 }
 
+// Tensor-core packs (modes 2 / 3, ungrouped) through a shared-memory tile: the parameter tensor is read in contiguous
+// runs ((co, ci) -> R*S consecutive floats, consecutive ci adjacent) and the pack written in 128-byte rows (mode 2: 32
+// consecutive ci of one (tap, co); mode 3: 32 consecutive co of one (flipped tap, ci)).  The elementwise kernel above
+// reads with a stride of R*S floats between neighbouring threads (~9x sector amplification on the 20 MB weights of the
+// deep levels); 136 pack launches were 2.7 % of the taichi@256 training step.
+__global__ void __launch_bounds__(256) k_pack_weight_tiled(const float* __restrict__ w, int Co, int Ci, int RS,
+                                                           const int* __restrict__ cin_map, int Cin_p, int Cout_p,
+                                                           int transposed, int x3, float* __restrict__ wp,
+                                                           long long total) {
+    extern __shared__ float tile[];            // [32 co][32 ci_p][RSp], RSp = RS | 1 (odd: conflict-free transposed reads)
+    const int RSp = RS | 1;
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    for (int idx = threadIdx.x; idx < 32 * 32 * RS; idx += 256) {
+        const int tap = idx % RS, ci_l = (idx / RS) & 31, co_l = idx / (RS * 32);
+        const int co = co0 + co_l, ci_p = ci0 + ci_l;
+        float v = 0.f;
+        if (co < Co && ci_p < Cin_p) {
+            const int ci = cin_map ? cin_map[ci_p] : ci_p;
+            if (ci >= 0 && ci < Ci) v = w[((long long)co * Ci + ci) * RS + tap];
+        }
+        tile[(co_l * 32 + ci_l) * RSp + tap] = v;
+    }
+    __syncthreads();
+    const int Kin = transposed ? Cout_p : Cin_p, Kout = transposed ? Cin_p : Cout_p;
+    __nv_bfloat16* cross = reinterpret_cast<__nv_bfloat16*>(wp + total);
+    for (int idx = threadIdx.x; idx < 32 * 32 * RS; idx += 256) {
+        const int in_l = idx & 31, out_l = (idx >> 5) & 31, tap = idx >> 10;   // in = the pack's contiguous (K) index
+        const int co_l = transposed ? in_l : out_l, ci_l = transposed ? out_l : in_l;
+        const int ki = (transposed ? co0 : ci0) + in_l, ko = (transposed ? ci0 : co0) + out_l;
+        if (ki >= Kin || ko >= Kout) continue;
+        const float v = tile[(co_l * 32 + ci_l) * RSp + (transposed ? RS - 1 - tap : tap)];   // dgrad: flipped kernel
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        const float hi = __uint_as_float(u);
+        wp[((long long)tap * Kout + ko) * Kin + ki] = hi;
+        if (x3) pack_cross(cross, (long long)tap * Kout + ko, ki, Kin, v, hi);
+    }
+}
+
 // mode 4: sub-pixel pack of a 3x3 kernel applied after a nearest x2 upsample (util.py:84-85).  For output parity
 // (py,px) the conv is a 2x2 conv of the low-resolution input whose taps are sums of the 3x3 taps:
 //   py = 0: rows {0} | {1,2}      py = 1: rows {0,1} | {2}        (same for columns)
@@ -498,6 +537,23 @@ MK_EXPORT int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int 
             k_pack_weight<<<(unsigned)mk_cdiv(Cout_p, 256), 256, 0, (cudaStream_t)stream>>>(
                 w, Co, Cig, R, S, groups, cin_map, Cin_p, Cout_p, 0, wpack, 0, bias, bias_p);
         return mk_check_launch("mk_pack_weight(ups)");
+    }
+    if ((mode & 6) == 2 && groups == 1 && R * S <= 16) {
+        const int RS = R * S;
+        dim3 grid((unsigned)mk_cdiv(Cin_p, 32), (unsigned)mk_cdiv(Cout_p, 32));
+        const size_t smem = (size_t)32 * 32 * (RS | 1) * sizeof(float);
+        static unsigned long long attr_done = 0;
+        if (const unsigned long long attr_bit = mk_attr_needed(attr_done)) {
+            cudaError_t e = cudaFuncSetAttribute(k_pack_weight_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+            if (e != cudaSuccess) { mk_set_error("mk_pack_weight: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
+            attr_done |= attr_bit;
+        }
+        k_pack_weight_tiled<<<grid, 256, smem, (cudaStream_t)stream>>>(w, Co, Cig, RS, cin_map, Cin_p, Cout_p, mode & 1,
+                                                                       (mode >> 3) & 1, wpack, total);
+        if (bias_p)  // zero-padded bias copy: the elementwise kernel with an empty weight range (total = 0)
+            k_pack_weight<<<(unsigned)mk_cdiv(Cout_p, 256), 256, 0, (cudaStream_t)stream>>>(
+                w, Co, Cig, R, S, groups, cin_map, Cin_p, Cout_p, 0, wpack, 0, bias, bias_p);
+        return mk_check_launch("mk_pack_weight(tiled)");
     }
     k_pack_weight<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         w, Co, Cig, R, S, groups, cin_map, Cin_p, Cout_p, mode, wpack, total, bias, bias_p);

@@ -151,7 +151,7 @@ def _times4_params(cp, device):
 
 def _channel_maps(segs, device):
     """(phys->logical int32 [Cp], logical->phys int32 [C]) device tensors for a segment tuple; None for identity."""
-    if len(segs) == 1 and segs[0][0] == segs[0][1]:
+    if all(logical == padded for logical, padded in segs):   # no padding holes anywhere: physical == logical
         return None, None
     key = (segs, device)
     if key not in _MAP_CACHE:
