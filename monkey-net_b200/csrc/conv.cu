@@ -9,7 +9,6 @@
 // that the parity tests pin to the oracle at 1e-5.
 #include "common.cuh"
 #include <cuda_bf16.h>
-#include <stdlib.h>
 
 struct ConvP {
     const float* x; int N, Hin, Win, Hl, Wl, Cin_p, ldx, ups;
@@ -412,6 +411,8 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (bias_p && i < Cout_p) bias_p[i] = (bias && i < Co) ? bias[i] : 0.f;
     if (i >= total) return;
+    // (a shared-memory-tiled variant with coalesced reads AND writes measured no faster in the step - 46.86 vs 46.74 ms,
+    //  the packs are latency-, not bandwidth-bound - and was dropped)
     // modes 2/3 = modes 0/1 in the tensor-core layout [tap][Kout][Kin] (K-major rows), values rounded to TF32;
     // bit 3 (mode | 8): reference-precision pack - behind the hi half (offset `total`) follows the CROSS operand of the
     // BF16 correction MMA (conv_halo.cu): [tap][Kout][Kin rounded up to 8] 4-byte slots, every group of 8 input
@@ -454,87 +455,34 @@ __global__ void k_pack_weight(const float* __restrict__ w, int Co, int Cig, int 
     wp[i] = v;
 }
 
-// Tensor-core packs (modes 2 / 3, ungrouped) through a shared-memory tile: the parameter tensor is read in contiguous
-// runs ((co, ci) -> R*S consecutive floats, consecutive ci adjacent) and the pack written in 128-byte rows (mode 2: 32
-// consecutive ci of one (tap, co); mode 3: 32 consecutive co of one (flipped tap, ci)).  The elementwise kernel above
-// reads with a stride of R*S floats between neighbouring threads (~9x sector amplification on the 20 MB weights of the
-// deep levels); 136 pack launches were 2.7 % of the taichi@256 training step.
-constexpr int PK_CO = 8;   // output channels per block: small tiles = many blocks (the pack is latency-bound, not bandwidth-bound)
-__global__ void __launch_bounds__(256) k_pack_weight_tiled(const float* __restrict__ w, int Co, int Ci, int RS,
-                                                           const int* __restrict__ cin_map, int Cin_p, int Cout_p,
-                                                           int transposed, int x3, float* __restrict__ wp,
-                                                           long long total) {
-    __shared__ float tile[PK_CO * 32 * 17];    // [co][32 ci_p][RSp], RSp = RS | 1 (odd: conflict-free transposed reads)
-    const int RSp = RS | 1;
-    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * PK_CO;
-    for (int idx = threadIdx.x; idx < PK_CO * 32 * RS; idx += 256) {
-        const int tap = idx % RS, ci_l = (idx / RS) & 31, co_l = idx / (RS * 32);
-        const int co = co0 + co_l, ci_p = ci0 + ci_l;
-        float v = 0.f;
-        if (co < Co && ci_p < Cin_p) {
-            const int ci = cin_map ? cin_map[ci_p] : ci_p;
-            if (ci >= 0 && ci < Ci) v = w[((long long)co * Ci + ci) * RS + tap];
-        }
-        tile[(co_l * 32 + ci_l) * RSp + tap] = v;
-    }
-    __syncthreads();
-    const int Kin = transposed ? Cout_p : Cin_p, Kout = transposed ? Cin_p : Cout_p;
-    const int IN = transposed ? PK_CO : 32, OUT = transposed ? 32 : PK_CO;   // extents of the pack's K / row index
-    __nv_bfloat16* cross = reinterpret_cast<__nv_bfloat16*>(wp + total);
-    for (int idx = threadIdx.x; idx < PK_CO * 32 * RS; idx += 256) {
-        const int in_l = idx % IN, out_l = (idx / IN) % OUT, tap = idx / (IN * OUT);
-        const int co_l = transposed ? in_l : out_l, ci_l = transposed ? out_l : in_l;
-        const int ki = (transposed ? co0 : ci0) + in_l, ko = (transposed ? ci0 : co0) + out_l;
-        if (ki >= Kin || ko >= Kout) continue;
-        const float v = tile[(co_l * 32 + ci_l) * RSp + (transposed ? RS - 1 - tap : tap)];   // dgrad: flipped kernel
-        uint32_t u;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-        const float hi = __uint_as_float(u);
-        wp[((long long)tap * Kout + ko) * Kin + ki] = hi;
-        if (x3) pack_cross(cross, (long long)tap * Kout + ko, ki, Kin, v, hi);
-    }
-}
-
 // mode 4: sub-pixel pack of a 3x3 kernel applied after a nearest x2 upsample (util.py:84-85).  For output parity
 // (py,px) the conv is a 2x2 conv of the low-resolution input whose taps are sums of the 3x3 taps:
 //   py = 0: rows {0} | {1,2}      py = 1: rows {0,1} | {2}        (same for columns)
-// Layout [parity = py*2+px][tap = r2*2+s2][Cout_p][Cin_p], rounded to TF32 after the sum; through the same
-// shared-memory tile as above: [32 co][32 ci_p][9] in, 16 (parity, tap) rows of 32 ci out.
-__global__ void __launch_bounds__(256) k_pack_weight_ups_tiled(const float* __restrict__ w, int Co, int Ci,
-                                                               const int* __restrict__ cin_map, int Cin_p, int Cout_p,
-                                                               float* __restrict__ wp, long long total, int x3) {
-    __shared__ float tile[PK_CO * 32 * 9];
-    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * PK_CO;
-    for (int idx = threadIdx.x; idx < PK_CO * 32 * 9; idx += 256) {
-        const int tap = idx % 9, ci_l = (idx / 9) & 31, co_l = idx / (9 * 32);
-        const int co = co0 + co_l, ci_p = ci0 + ci_l;
-        float v = 0.f;
-        if (co < Co && ci_p < Cin_p) {
-            const int ci = cin_map ? cin_map[ci_p] : ci_p;
-            if (ci >= 0 && ci < Ci) v = w[((long long)co * Ci + ci) * 9 + tap];
-        }
-        tile[idx] = v;
-    }
-    __syncthreads();
-    __nv_bfloat16* cross = reinterpret_cast<__nv_bfloat16*>(wp + total);
-    for (int idx = threadIdx.x; idx < PK_CO * 32 * 16; idx += 256) {
-        const int ci_l = idx & 31, co_l = (idx >> 5) % PK_CO, t = idx / (32 * PK_CO);
-        const int ci_p = ci0 + ci_l, co = co0 + co_l;
-        if (ci_p >= Cin_p || co >= Cout_p) continue;
-        const int tap = t & 3, par = t >> 2;
-        const int py = par >> 1, px = par & 1, r2 = tap >> 1, s2 = tap & 1;
+// Layout [parity = py*2+px][tap = r2*2+s2][Cout_p][Cin_p], rounded to TF32 after the sum.
+__global__ void k_pack_weight_ups(const float* __restrict__ w, int Co, int Ci, const int* __restrict__ cin_map,
+                                  int Cin_p, int Cout_p, float* __restrict__ wp, long long total, int x3) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ci_p = (int)(i % Cin_p);
+    long long t = i / Cin_p;
+    const int co = (int)(t % Cout_p);
+    t /= Cout_p;
+    const int tap = (int)(t & 3), par = (int)(t >> 2);
+    const int py = par >> 1, px = par & 1, r2 = tap >> 1, s2 = tap & 1;
+    const int ci = cin_map ? cin_map[ci_p] : ci_p;
+    float v = 0.f;
+    if (co < Co && ci >= 0 && ci < Ci) {
         const int r_lo = py == 0 ? (r2 == 0 ? 0 : 1) : (r2 == 0 ? 0 : 2), r_hi = py == 0 ? (r2 == 0 ? 0 : 2) : (r2 == 0 ? 1 : 2);
         const int s_lo = px == 0 ? (s2 == 0 ? 0 : 1) : (s2 == 0 ? 0 : 2), s_hi = px == 0 ? (s2 == 0 ? 0 : 2) : (s2 == 0 ? 1 : 2);
-        const float* wk = tile + (co_l * 32 + ci_l) * 9;
-        float v = 0.f;
+        const float* wk = w + ((long long)co * Ci + ci) * 9;
         for (int r = r_lo; r <= r_hi; ++r)
             for (int sx = s_lo; sx <= s_hi; ++sx) v += wk[r * 3 + sx];
-        uint32_t u;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-        const float hi = __uint_as_float(u);
-        wp[((long long)t * Cout_p + co) * Cin_p + ci_p] = hi;
-        if (x3) pack_cross(cross, (long long)t * Cout_p + co, ci_p, Cin_p, v, hi);
     }
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    const float hi = __uint_as_float(u);
+    wp[i] = hi;
+    if (x3) pack_cross(reinterpret_cast<__nv_bfloat16*>(wp + total), t * Cout_p + co, ci_p, Cin_p, v, hi);
 }
 
 MK_EXPORT int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int groups, const int* cin_map,
@@ -546,28 +494,12 @@ MK_EXPORT int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int 
     if ((mode & 7) == 4) {
         MK_REQUIRE(R == 3 && S == 3 && groups == 1, "mk_pack_weight mode 4: 3x3 ungrouped kernels only");
         total = 16LL * Cin_p * Cout_p;
-        dim3 grid((unsigned)mk_cdiv(Cin_p, 32), (unsigned)mk_cdiv(Cout_p, PK_CO));
-        k_pack_weight_ups_tiled<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Co, Cig, cin_map, Cin_p, Cout_p, wpack, total,
-                                                                        (mode >> 3) & 1);
+        k_pack_weight_ups<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Co, Cig, cin_map, Cin_p,
+                                                                                           Cout_p, wpack, total, mode >> 3);
         if (bias_p)  // zero-padded bias copy: the regular kernel with an empty weight range (total = 0)
             k_pack_weight<<<(unsigned)mk_cdiv(Cout_p, 256), 256, 0, (cudaStream_t)stream>>>(
                 w, Co, Cig, R, S, groups, cin_map, Cin_p, Cout_p, 0, wpack, 0, bias, bias_p);
         return mk_check_launch("mk_pack_weight(ups)");
-    }
-    static int tiled_env = -1;   // experiments: MONKEY_B200_PACK_TILED = 0 selects the elementwise kernel
-    if (tiled_env < 0) {
-        const char* e = getenv("MONKEY_B200_PACK_TILED");
-        tiled_env = e ? atoi(e) : 1;
-    }
-    if (tiled_env && (mode & 6) == 2 && groups == 1 && R * S <= 16) {
-        const int RS = R * S;
-        dim3 grid((unsigned)mk_cdiv(Cin_p, 32), (unsigned)mk_cdiv(Cout_p, PK_CO));
-        k_pack_weight_tiled<<<grid, 256, 0, (cudaStream_t)stream>>>(w, Co, Cig, RS, cin_map, Cin_p, Cout_p, mode & 1,
-                                                                       (mode >> 3) & 1, wpack, total);
-        if (bias_p)  // zero-padded bias copy: the elementwise kernel with an empty weight range (total = 0)
-            k_pack_weight<<<(unsigned)mk_cdiv(Cout_p, 256), 256, 0, (cudaStream_t)stream>>>(
-                w, Co, Cig, R, S, groups, cin_map, Cin_p, Cout_p, 0, wpack, 0, bias, bias_p);
-        return mk_check_launch("mk_pack_weight(tiled)");
     }
     k_pack_weight<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
         w, Co, Cig, R, S, groups, cin_map, Cin_p, Cout_p, mode, wpack, total, bias, bias_p);
