@@ -69,6 +69,10 @@ int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int groups, co
  * cin_inv[Ci] maps each LOGICAL input channel to its physical position (NULL = identity). */
 int mk_unpack_wgrad(const float* dwpack, int Co, int Cig, int R, int S, int groups, const int* cin_inv, int Cin_p,
                     int Cout_p, float* dw, void* stream);
+/* the same, accumulating (+=) into the parameter's gradient tensor `grad` (parameter layout): autograd's
+ * AccumulateGrad for conv weights done by the unpack kernel itself (torch/autograd: one add kernel per parameter). */
+int mk_unpack_wgrad_acc(const float* dwpack, int Co, int Cig, int R, int S, int groups, const int* cin_inv, int Cin_p,
+                        int Cout_p, float* grad, void* stream);
 /* dz = dy * y * (1 - y)  (backward of the fused sigmoid epilogue, generator.py:80); n floats, n % 4 == 0 */
 int mk_sigmoid_bwd(const float* y, const float* dy, float* dz, long long n, void* stream);
 /* y = epilogue(conv(x)); implicit GEMM, fp32 FFMA (exact-parity path).

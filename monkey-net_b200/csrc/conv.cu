@@ -506,6 +506,7 @@ MK_EXPORT int mk_pack_weight(const float* w, int Co, int Cig, int R, int S, int 
     return mk_check_launch("mk_pack_weight");
 }
 
+template <bool ACC>
 __global__ void k_unpack_wgrad(const float* __restrict__ dwp, int Co, int Cig, int R, int S, int groups,
                                const int* __restrict__ cin_inv, int Cin_p, int Cout_p, float* __restrict__ dw,
                                long long total) {
@@ -520,7 +521,8 @@ __global__ void k_unpack_wgrad(const float* __restrict__ dwp, int Co, int Cig, i
     int cog = Co / groups;
     int ci = (co / cog) * Cig + cil;        // logical input channel
     int ci_p = cin_inv ? cin_inv[ci] : ci;  // physical position
-    dw[i] = dwp[((long long)(r * S + s) * Cin_p + ci_p) * Cout_p + co];
+    const float v = dwp[((long long)(r * S + s) * Cin_p + ci_p) * Cout_p + co];
+    if (ACC) dw[i] += v; else dw[i] = v;
 }
 
 // cin_map here is the INVERSE map (logical -> physical), length = logical Cin.
@@ -528,7 +530,18 @@ MK_EXPORT int mk_unpack_wgrad(const float* dwpack, int Co, int Cig, int R, int S
                               int Cin_p, int Cout_p, float* dw, void* stream) {
     long long total = (long long)Co * Cig * R * S;
     if (total == 0) return 0;
-    k_unpack_wgrad<<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dwpack, Co, Cig, R, S, groups,
-                                                                                     cin_inv, Cin_p, Cout_p, dw, total);
+    k_unpack_wgrad<false><<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        dwpack, Co, Cig, R, S, groups, cin_inv, Cin_p, Cout_p, dw, total);
     return mk_check_launch("mk_unpack_wgrad");
+}
+
+// Same, ACCUMULATING into `grad` (the parameter's .grad tensor, parameter layout): the weight gradient goes from the packed
+// GEMM result straight into the optimiser's flat gradient buffer - no temporary and no separate add kernel per parameter.
+MK_EXPORT int mk_unpack_wgrad_acc(const float* dwpack, int Co, int Cig, int R, int S, int groups, const int* cin_inv,
+                                  int Cin_p, int Cout_p, float* grad, void* stream) {
+    long long total = (long long)Co * Cig * R * S;
+    if (total == 0) return 0;
+    k_unpack_wgrad<true><<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        dwpack, Co, Cig, R, S, groups, cin_inv, Cin_p, Cout_p, grad, total);
+    return mk_check_launch("mk_unpack_wgrad_acc");
 }

@@ -261,6 +261,32 @@ def from_nhwc(a, B):
 
 
 # ====================================================================================================== convolution
+# Direct parameter gradients: inside `direct_param_grads()` the conv weight gradient is ACCUMULATED by the unpack kernel
+# straight into `weight.grad` (when that tensor exists, e.g. FlatAdam's views of its flat gradient buffer, zeroed by the
+# fused Adam launch) and autograd receives None for the weight - the same accumulate-into-.grad semantics as
+# AccumulateGrad, minus one temporary and one `add_` launch per parameter (62 of the 247 ATen elementwise launches of a
+# taichi training iteration).  Only meaningful under `.backward()`; never enabled for `torch.autograd.grad` callers.
+_DIRECT_GRAD = [0]
+
+
+class direct_param_grads:
+    def __enter__(self):
+        _DIRECT_GRAD[0] += 1
+
+    def __exit__(self, *exc):
+        _DIRECT_GRAD[0] -= 1
+        return False
+
+
+def _direct_grad_target(param):
+    if _DIRECT_GRAD[0] <= 0:
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape or g.device != param.device:
+        return None
+    return g
+
+
 class _Conv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, resid, segs, pad, groups, ups, act, pool, mode, bias_grad_zero=False):
@@ -360,8 +386,15 @@ class _Conv(torch.autograd.Function):
             else:
                 lib.call('mk_conv2d_wgrad', x.data_ptr(), N, Hin, Win, Cp, Cp, ups, dy.data_ptr(), Cop, Cop, R, S, pad,
                          dwp.data_ptr(), st)
-            dw = torch.empty_like(weight)
-            lib.call('mk_unpack_wgrad', dwp.data_ptr(), Co, Cig, R, S, groups, _ptr(cinv), Cp, Cop, dw.data_ptr(), st)
+            tgt = _direct_grad_target(weight)
+            if tgt is not None:
+                # the optimiser's gradient buffer is the destination: no temporary, no AccumulateGrad add kernel
+                lib.call('mk_unpack_wgrad_acc', dwp.data_ptr(), Co, Cig, R, S, groups, _ptr(cinv), Cp, Cop,
+                         tgt.data_ptr(), st)
+            else:
+                dw = torch.empty_like(weight)
+                lib.call('mk_unpack_wgrad', dwp.data_ptr(), Co, Cig, R, S, groups, _ptr(cinv), Cp, Cop, dw.data_ptr(),
+                         st)
         if has_bias and ctx.needs_input_grad[2] and not ctx.bias_grad_zero:
             sums = _empty(2 * Cop, like=x)
             lib.call('mk_colstats', dy.data_ptr(), Cop, N, dy.shape[1] * dy.shape[2], Cop, 0, sums.data_ptr(), st)

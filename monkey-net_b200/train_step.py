@@ -104,12 +104,14 @@ def _train_iteration_flat(generator_full_par, discriminator_full_par, optimizers
     stream concurrently with the whole discriminator step and are joined at the end of the iteration - the collective
     is off the critical path (fork / join is captured in the CUDA graph as stream dependencies)."""
     from . import dist as mkdist
+    from . import ops as mkops
     opt_g, opt_d, opt_kp = optimizers
     out = generator_full_par(x)
     loss_values = [val.mean() for val in out[:-2]]
     generated, kp_joined = out[-2], out[-1]
     loss = sum(loss_values)
-    loss.backward(retain_graph=not train_params['detach_kp_discriminator'])
+    with mkops.direct_param_grads():   # conv weight gradients accumulate straight into FlatAdam's gradient buffers
+        loss.backward(retain_graph=not train_params['detach_kp_discriminator'])
     overlap = mkdist.world() > 1 and train_params['detach_kp_discriminator'] and loss.is_cuda
     side = None
     if overlap:
@@ -127,7 +129,8 @@ def _train_iteration_flat(generator_full_par, discriminator_full_par, optimizers
     g_vals = loss_values
     loss_values = [val.mean() for val in discriminator_full_par(x, kp_joined, generated)]
     loss = sum(loss_values)
-    loss.backward()
+    with mkops.direct_param_grads():
+        loss.backward()
     opt_d.sync_gradients(); opt_d.step()
     if not train_params['detach_kp_discriminator']:
         opt_kp.sync_gradients(); opt_kp.step()
