@@ -123,6 +123,15 @@ int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin_p, int ld
 int mk_conv2d_tc_halo_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc, int R,
                          int S, int pad, const float* scale, const float* shift, const float* resid, int ldr, int act,
                          float slope, float* y, int Cout_p, int ldy, void* stream);
+/* conv3x3(nearest_x2(x)), pad 1 (modules/util.py:84-85) on the halo-window kernel: four sub-pixel 2x2 passes over the
+ * low-resolution grid, each storing its output parity through a 5-D TMA map.  wpack_ups = mk_pack_weight mode 4 (| 8 for
+ * the _x3 entry); y [N][2 Hin][2 Win][ldy].  -2 (nothing launched) outside the envelope: callers use mk_conv2d_tc(ups=1). */
+int mk_conv2d_tc_halo_ups(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_ups,
+                          const float* scale, const float* shift, int act, float slope, float* y, int Cout_p, int ldy,
+                          void* stream);
+int mk_conv2d_tc_halo_ups_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_ups,
+                             const float* scale, const float* shift, int act, float slope, float* y, int Cout_p, int ldy,
+                             void* stream);
 /* dry run of its planner: out[16] = grid.x, cout tiles, RB, smem bytes, halo stages, weight slots, resident?, TMEM
  * columns, tiles, halo rows, halo stage bytes, weight slot bytes, valid tile width, output groups, acc columns, x3 */
 int mk_conv2d_tc_halo_plan(int N, int Hin, int Win, int Cin_p, int R, int S, int pad, int Cout_p, int has_resid, int x3,

@@ -65,7 +65,8 @@ constexpr int H_THREADS = 384;
 constexpr int H_FIXED = 3072;   // barriers (<= 848 B) + the CTA's scale / shift vectors (1 KB) + 1023 B alignment slack
 
 struct HP {
-    int N, Ho, Wo, Cout_p, Cin_p, R, S, pad;
+    int N, Ho, Wo, Cout_p, Cin_p, R, S, pad_h, pad_w;
+    int ups, py, px;       // sub-pixel pass of conv3x3(nearest_x2(x)): 2x2 conv on the low-res grid, output parity (py, px)
     int TWv, RB, tilesW, tilesH, ntiles;
     int halo_rows, a_half, a_stage, a_stages;
     int b_rows, b_half, b_tx, b_slot, b_slots, resident;   // b_tx = bytes one weight TMA box delivers
@@ -78,6 +79,11 @@ struct HP {
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                  : "memory");
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -237,7 +243,7 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const int as = ai % p.a_stages;
                     mbar_wait(&a_empty[as], ((ai / p.a_stages) & 1) ^ 1);
                     mbar_expect_tx(&a_full[as], p.a_half);
-                    tma_load_4d(a_ring + as * p.a_stage, &tmA, &a_full[as], ch * HK, w0 - p.pad, h0 - p.pad, n);
+                    tma_load_4d(a_ring + as * p.a_stage, &tmA, &a_full[as], ch * HK, w0 - p.pad_w, h0 - p.pad_h, n);
                     if (!p.resident || lt > 0) continue;
                     for (int tap = 0; tap < ntaps; ++tap) {
                         const int bs = ch * ntaps + tap;
@@ -488,7 +494,9 @@ k_conv_halo(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     if (leader && p.nstg == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     epi_bar();
                     if (leader) {
-                        tma_store_4d(&tmY, sbuf, cout0 + cbase, w0, h0 + 8 * rb, n);
+                        // sub-pixel pass: the output is seen as (c, px, w, py, n * H + h) with the full-resolution strides
+                        if (p.ups) tma_store_5d(&tmY, sbuf, cout0 + cbase, p.px, w0, p.py, n * p.Ho + h0 + 8 * rb);
+                        else tma_store_4d(&tmY, sbuf, cout0 + cbase, w0, h0 + 8 * rb, n);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -537,18 +545,29 @@ static bool halo_wants_ct(int R, int S, int Cin_p, int Cout_p, int x3) {
     return t_ct < 0.95 * t_plain;
 }
 
+static thread_local int t_hups = -1;   // >= 0: sub-pixel pass (parity py * 2 + px) of the upsampled conv, set by mk_conv2d_tc_halo_ups
+
 static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_tc,
                           int R, int S, int pad, const float* scale, const float* shift, const float* resid,
                           int ldr, int act, float slope, float* y, int Cout_p, int ldy, void* stream) {
-    const int Ho = Hin + 2 * pad - R + 1, Wo = Win + 2 * pad - S + 1;
-    if (Cin_p % 4 || ldx % 4 || Cout_p % 4 || ldy % 4 || (resid && ldr % 4) || R != S || (R != 1 && R != 3 && R != 4) ||
+    const int ups_par = t_hups;
+    // sub-pixel pass: a 2x2 conv on the LOW-resolution grid (output tile grid = input grid), rows {h-1, h} for py = 0 and
+    // {h, h+1} for py = 1 (same for columns): an asymmetric "padding" of 1 - py / 1 - px before the first tap
+    const int Ho = ups_par >= 0 ? Hin : Hin + 2 * pad - R + 1, Wo = ups_par >= 0 ? Win : Win + 2 * pad - S + 1;
+    if (Cin_p % 4 || ldx % 4 || Cout_p % 4 || ldy % 4 || (resid && ldr % 4) || R != S ||
+        (R != 1 && R != 3 && R != 4 && !(R == 2 && ups_par >= 0)) || (ups_par >= 0 && (R != 2 || resid || Hin % 8)) ||
         Ho < 1 || Wo < 1) {
         mk_set_error("mk_conv2d_tc_halo: outside the halo kernel's envelope");
         return -2;
     }
     HP p;
     p.x3 = t_hx3;
-    p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout_p = Cout_p; p.Cin_p = Cin_p; p.R = R; p.S = S; p.pad = pad;
+    p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout_p = Cout_p; p.Cin_p = Cin_p; p.R = R; p.S = S;
+    p.ups = ups_par >= 0 ? 1 : 0;
+    p.py = p.ups ? (ups_par >> 1) : 0;
+    p.px = p.ups ? (ups_par & 1) : 0;
+    p.pad_h = p.ups ? 1 - p.py : pad;
+    p.pad_w = p.ups ? 1 - p.px : pad;
     p.TWv = 16 - (S - 1);
     p.tilesW = (Wo + p.TWv - 1) / p.TWv;
     p.nchunks = (Cin_p + HK - 1) / HK;
@@ -585,6 +604,7 @@ static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, in
         if (!p.ct && force_rb && rb != force_rb && !(rb == 1 && 2 * force_rb * p.npad > 512)) continue;
         if (2 * rb * p.npad > 512) break;                        // double-buffered accumulators in TMEM
         if (rb > 1 && 8 * (rb / 2) >= Ho) break;                           // the extra row-blocks would all be empty
+        if (p.ups && Ho % (8 * rb)) break;                                  // (n, h) are one merged store dimension: no partial tiles
         const int halo_rows = 8 * rb + R;                                   // (R-1) halo rows + 1 overrun row
         const int a_stage = (halo_rows * 16 * 128) << p.x3;
         int nstg = 0, res = 0, bslots = 0;
@@ -706,7 +726,10 @@ static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, in
         // CT: one box = the S column taps of a tap row, rows s * Cout_p + co
         cuuint32_t box[3] = {(cuuint32_t)HK, (cuuint32_t)(p.ct ? Cout_p : p.b_rows), (cuuint32_t)(p.ct ? S : 1)};
         cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wpack_tc), dims, strides, box,
+        // sub-pixel pass: the mode-4 pack is [parity][2x2 tap][Cout_p][Cin_p] (16 taps) + its cross operand behind it
+        const size_t par_taps = p.ups ? (size_t)(p.py * 2 + p.px) * 4 : 0, all_taps = p.ups ? 16 : (size_t)R * S;
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                            const_cast<float*>(wpack_tc) + par_taps * Cout_p * Cin_p, dims, strides, box,
                             es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: weight tensor map rejected (%d)", (int)r);
@@ -718,12 +741,25 @@ static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, in
             cuuint64_t dims2[3] = {cin8, (cuuint64_t)Cout_p, (cuuint64_t)(R * S)};
             cuuint64_t strides2[2] = {cin8 * 4, cin8 * Cout_p * 4};
             r = encode(&tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
-                       const_cast<float*>(wpack_tc) + (size_t)R * S * Cout_p * Cin_p, dims2, strides2, box, es,
+                       const_cast<float*>(wpack_tc) + all_taps * Cout_p * Cin_p + par_taps * Cout_p * cin8, dims2, strides2, box, es,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: cross-operand tensor map rejected (%d)", (int)r);
         }
     }
+    if (p.ups) {
+        // y[n][2h + py][2w + px][c] as (c, px, w, py, n * H + h): the frame stride (2H)(2W) ld equals H times the stride of h
+        cuuint64_t dims[5] = {(cuuint64_t)Cout_p, 2, (cuuint64_t)Wo, 2, (cuuint64_t)N * Ho};
+        cuuint64_t strides[4] = {(cuuint64_t)ldy * 4, (cuuint64_t)2 * ldy * 4, (cuuint64_t)2 * Wo * ldy * 4,
+                                 (cuuint64_t)4 * Wo * ldy * 4};
+        cuuint32_t box[5] = {32, 1, (cuuint32_t)p.TWv, 1, 8};
+        cuuint32_t es5[5] = {1, 1, 1, 1, 1};
+        CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, y, dims, strides, box, es5,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MK_REQUIRE(r == CUDA_SUCCESS, "mk_conv2d_tc_halo: sub-pixel output tensor map rejected (%d)", (int)r);
+        tmR = tmY;
+    } else
     for (int which = 0; which < 2; ++which) {
         if (which == 1 && !resid) { tmR = tmY; break; }
         const float* base = which ? resid : y;
@@ -753,6 +789,7 @@ static int halo_conv_impl(const float* x, int N, int Hin, int Win, int Cin_p, in
     do {                                                                                    \
         if (R == 3 && S == 3) { if (p.ct) HALO_LAUNCH(3, 3, XX, RE, true); else HALO_LAUNCH(3, 3, XX, RE, false); } \
         else if (R == 4 && S == 4) { if (p.ct) HALO_LAUNCH(4, 4, XX, RE, true); else HALO_LAUNCH(4, 4, XX, RE, false); } \
+        else if (R == 2 && S == 2) { if (p.ct) HALO_LAUNCH(2, 2, XX, RE, true); else HALO_LAUNCH(2, 2, XX, RE, false); } \
         else HALO_LAUNCH(1, 1, XX, RE, false);                                              \
     } while (0)
     if (p.x3) { if (p.resident) HALO_RS(true, true); else HALO_RS(true, false); }
@@ -775,6 +812,43 @@ MK_EXPORT int mk_conv2d_tc_halo(const float* x, int N, int Hin, int Win, int Cin
                             Cout_p, ldy, stream);
     }
     t_hct = 0;
+    return rc;
+}
+
+// conv3x3(nearest_x2(x)), pad 1 (modules/util.py:84-85), as four sub-pixel 2x2 halo-window passes on the low-resolution
+// grid: `wpack_ups` is the mode-4 pack of mk_pack_weight ([parity][2x2 tap][Cout_p][Cin_p], | 8 for reference precision),
+// y is [N][2 Hin][2 Win][ldy].  Returns -2 (before launching anything) outside the envelope (Hin % 8, few tiles ...).
+MK_EXPORT int mk_conv2d_tc_halo_ups(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_ups,
+                                    const float* scale, const float* shift, int act, float slope, float* y, int Cout_p,
+                                    int ldy, void* stream) {
+    int rc = 0;
+    for (int par = 0; par < 4 && rc == 0; ++par) {
+        t_hups = par;
+        t_hct = halo_wants_ct(2, 2, Cin_p, Cout_p, t_hx3) ? 1 : 0;
+        rc = halo_conv_impl(x, N, Hin, Win, Cin_p, ldx, wpack_ups, 2, 2, 0, scale, shift, nullptr, 0, act, slope, y, Cout_p,
+                            ldy, stream);
+        if (rc == -2 && t_hct) {
+            t_hct = 0;
+            rc = halo_conv_impl(x, N, Hin, Win, Cin_p, ldx, wpack_ups, 2, 2, 0, scale, shift, nullptr, 0, act, slope, y,
+                                Cout_p, ldy, stream);
+        }
+        if (rc == -2 && par > 0) {   // all four passes share one plan: a later refusal would leave y half written
+            mk_set_error("mk_conv2d_tc_halo_ups: parity %d refused after parity 0 was launched", par);
+            rc = -1;
+        }
+    }
+    t_hups = -1;
+    t_hct = 0;
+    return rc;
+}
+
+MK_EXPORT int mk_conv2d_tc_halo_ups_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* wpack_ups,
+                                       const float* scale, const float* shift, int act, float slope, float* y,
+                                       int Cout_p, int ldy, void* stream) {
+    t_hx3 = 1;
+    const int rc = mk_conv2d_tc_halo_ups(x, N, Hin, Win, Cin_p, ldx, wpack_ups, scale, shift, act, slope, y, Cout_p, ldy,
+                                         stream);
+    t_hx3 = 0;
     return rc;
 }
 

@@ -94,6 +94,7 @@ def conv_mode():
 # point declines (-2, before touching device state) shapes outside its envelope and few-tile layers, which run on
 # mk_conv2d_tc (split-K).  MONKEY_B200_CONV_HALO=0 switches it off.
 CONV_HALO = os.environ.get('MONKEY_B200_CONV_HALO', '1') != '0'
+CONV_HALO_UPS = os.environ.get('MONKEY_B200_CONV_HALO_UPS', '1') != '0'   # the upsampled convs on the halo kernel (A/B switch)
 
 
 def _tc_pack_numel(taps, kout, kin, x3):
@@ -110,6 +111,12 @@ def _tc_launch(xp, N, Hin, Win, Cp, ups, wp, R, S, pad, scale, shift, resid_ptr,
     if CONV_HALO and not ups:
         rc = lib.call_soft('mk_conv2d_tc_halo_x3' if x3 else 'mk_conv2d_tc_halo', (-2,), xp, N, Hin, Win, Cp, Cp, wp,
                            R, S, pad, scale, shift, resid_ptr, ldr, act, slope, yp, Cop, Cop, st)
+        if rc == 0:
+            return
+    elif CONV_HALO and CONV_HALO_UPS and resid_ptr is None:
+        # conv3x3(nearest_x2(x)): four sub-pixel 2x2 passes of the halo kernel on the low-resolution grid
+        rc = lib.call_soft('mk_conv2d_tc_halo_ups_x3' if x3 else 'mk_conv2d_tc_halo_ups', (-2,), xp, N, Hin, Win, Cp, Cp,
+                           wp, scale, shift, act, slope, yp, Cop, Cop, st)
         if rc == 0:
             return
     lib.call('mk_conv2d_tc_x3' if x3 else 'mk_conv2d_tc', xp, N, Hin, Win, Cp, Cp, ups, wp, R, S, pad, scale, shift,
@@ -477,10 +484,19 @@ def _infer_pack(weight, bias, segs, groups, ups, norm, Cp, tc, x3=False):
     return val
 
 
-def _tc_would_split(npix, cop, niter):
-    """mirror of mk_conv2d_tc's split-K decision (conv_tc.cu): few tiles and a linear epilogue"""
-    tiles = ((npix + 127) // 128) * ((cop + 127) // 128)
-    return tiles * 2 <= 148 and niter >= 4
+_SPLIT_CACHE = {}
+
+
+def _tc_would_split(N, Hin, Win, Cp, ups, R, S, pad, Cop):
+    """would mk_conv2d_tc run this layer split-K with a linear epilogue?  Asked from the library's own planner
+    (mk_conv2d_tc_plan: a host-side dry run, no launch) instead of re-deriving its rule here."""
+    key = (N, Hin, Win, Cp, ups, R, S, pad, Cop)
+    if key not in _SPLIT_CACHE:
+        import ctypes
+        out = (ctypes.c_int * 16)()
+        lib.query('mk_conv2d_tc_plan', N, Hin, Win, Cp, ups, R, S, pad, 0, Cop, Cop, out)
+        _SPLIT_CACHE[key] = out[5] > 1
+    return _SPLIT_CACHE[key]
 
 
 def conv_infer(a, weight, bias, pad, groups=1, ups=False, resid=None, act=0, slope=0.0, pool=0, norm=None):
@@ -521,10 +537,8 @@ def conv_bn_relu(a, conv_mod, norm_mod, pad, groups=1, ups=False, pool=0, extras
         N, Hin, Win, Cp = a.t.shape
         Co, _, _, R, S = conv_mod.weight.shape
         u = int(bool(ups))
-        npix = N * Hin * Win if u else N * ((Hin + 2 * pad - R + 1) * (Win + 2 * pad - S + 1))
-        niter = (4 if u else R * S) * ((Cp + 31) // 32)
         tc = _tc_ok(Cp, pad4(Co), u, 0, R, groups)
-        if not (tc and _tc_would_split(npix, pad4(Co), niter)):
+        if not (tc and _tc_would_split(N, Hin, Win, Cp, u, R, S, pad, pad4(Co))):
             y = conv_infer(a, conv_mod.weight, conv_mod.bias, pad, groups=groups, ups=ups, act=1, slope=0.0,
                            pool=pool, norm=norm_mod)
             return norm_act(y, None, mode='none', extras=extras) if extras else y

@@ -118,6 +118,53 @@ def test_conv_upsampled_matches_torch(cin, cout, H, W, N, kernel):
     assert err < KERNEL_TOL[kernel] * (2 if kernel == 'tf32x3' else 1), err
 
 
+@pytest.mark.parametrize('x3', [False, True])
+@pytest.mark.parametrize('cin,cout,H,W,N,act', [(128, 32, 64, 64, 8, 0),     # Cout 32: column taps on N (2 x 32)
+                                                (140, 32, 64, 64, 8, 1),     # 5 channel chunks, leaky epilogue
+                                                (64, 64, 32, 48, 16, 0),     # non-square, 3 + 1 column tiles
+                                                (36, 12, 64, 64, 8, 2),      # Cout_p = 12, sigmoid
+                                                (256, 160, 32, 32, 16, 0)])  # two cout tiles, streamed weights
+def test_conv_upsampled_halo_matches_torch(cin, cout, H, W, N, act, x3):
+    """mk_conv2d_tc_halo_ups: conv3x3(nearest_x2(x)) as four sub-pixel 2x2 halo-window passes (5-D TMA store of each
+    output parity) == F.interpolate + F.conv2d in double."""
+    from monkey_net_b200 import lib
+    torch.manual_seed(cin + cout)
+    dev = torch.device('cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(N, H, W, cin, device=dev)
+    w = torch.randn(cout, cin, 1, 3, 3, device=dev) / (cin * 9) ** 0.5
+    b = torch.randn(cout, device=dev)
+    wp = torch.empty(16 * cout * (cin + (((cin + 7) & ~7) if x3 else 0)), device=dev)
+    bp = torch.empty(cout, device=dev)
+    lib.call('mk_pack_weight', w.data_ptr(), cout, cin, 3, 3, 1, None, cin, cout, 4 | (8 if x3 else 0), wp.data_ptr(),
+             b.data_ptr(), bp.data_ptr(), st)
+    y = torch.full((N, 2 * H, 2 * W, cout), float('nan'), device=dev)
+    lib.call('mk_conv2d_tc_halo_ups_x3' if x3 else 'mk_conv2d_tc_halo_ups', x.data_ptr(), N, H, W, cin, cin, wp.data_ptr(),
+             None, bp.data_ptr(), act, 0.2, y.data_ptr(), cout, cout, st)
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any(), 'sub-pixel halo passes left outputs unwritten'
+    ref = _torch_conv(x, w, b, 1, None, act, ups=True) if act != 1 else None
+    if act == 1:   # leaky slope 0.2
+        r0 = _torch_conv(x, w, b, 1, None, 0, ups=True)
+        ref = torch.where(r0 > 0, r0, 0.2 * r0)
+    err = float((y.double() - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+    assert err < KERNEL_TOL['tf32x3' if x3 else 'tf32'] * (2 if x3 else 1), err
+
+
+def test_conv_upsampled_halo_declines_ragged_heights():
+    """(n, h) are one merged dimension of the sub-pixel store map: heights that are not multiples of 8 are refused (-2)
+    before anything is launched"""
+    from monkey_net_b200 import lib
+    dev = torch.device('cuda')
+    x = torch.randn(8, 60, 64, 64, device=dev)
+    y = torch.zeros(8, 120, 128, 32, device=dev)
+    wp = torch.zeros(16 * 32 * 64, device=dev)
+    rc = lib.call_soft('mk_conv2d_tc_halo_ups', (-2,), x.data_ptr(), 8, 60, 64, 64, 64, wp.data_ptr(), None, None, 0, 0.0,
+                       y.data_ptr(), 32, 32, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rc == -2 and float(y.abs().max()) == 0.0
+
+
 WGRAD_CASES = [(32, 64, 3, 1, 16, 16, 4), (64, 128, 3, 1, 32, 32, 2),
                (16, 32, 3, 1, 64, 64, 2), (48, 144, 3, 1, 13, 9, 3),
                (256, 256, 3, 1, 4, 4, 8), (512, 128, 3, 1, 2, 2, 32),
