@@ -41,7 +41,8 @@ METRIC = 'frames/sec (training step: G fwd+bwd+Adam, D fwd+bwd+Adam)'
 DEFAULT = {'config': 'taichi', 'res': 256, 'batch': 8}
 CONV_ENTRIES = ('mk_conv2d', 'mk_conv2d_wgrad', 'mk_conv2d_tc', 'mk_conv2d_wgrad_tc', 'mk_conv2d_tc_x3',
                 'mk_conv2d_wgrad_tc_x3', 'mk_conv2d_tc_halo', 'mk_conv2d_tc_halo_x3', 'mk_conv2d_wgrad_halo',
-                'mk_conv2d_wgrad_halo_x3', 'mk_conv2d_tc_halo_ups', 'mk_conv2d_tc_halo_ups_x3')
+                'mk_conv2d_wgrad_halo_x3', 'mk_conv2d_tc_halo_ups', 'mk_conv2d_tc_halo_ups_x3', 'mk_conv2d_wgrad_halo_ups',
+                'mk_conv2d_wgrad_halo_ups_x3')
 
 
 def parse():

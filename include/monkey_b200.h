@@ -155,6 +155,17 @@ int mk_conv2d_wgrad_halo(const float* x, int N, int Hin, int Win, int Cin_p, int
                          int ldy, int R, int S, int pad, float* dwpack, void* stream);
 int mk_conv2d_wgrad_halo_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
                             int ldy, int R, int S, int pad, float* dwpack, void* stream);
+/* weight gradient of conv3x3(nearest_x2(x)), pad 1, as four sub-pixel passes on the LOW-resolution grid (16 tap-pixel
+ * products per low-res pixel instead of 36 at full resolution, no upsampled copy of x): x [N][Hin][Win][ldx],
+ * dy [N][2 Hin][2 Win][ldy] read through a 5-D TMA map; dwpack_ups [16 = parity x 2x2 tap][Cin_p][Cout_p] is the gradient
+ * of the mode-4 pack, folded onto the parameter's 3x3 taps by mk_unpack_wgrad_ups (accumulate != 0: += into `dw`).
+ * -2 (nothing launched) outside the envelope (Hin % 8, few tiles): callers upsample x and use mk_conv2d_wgrad_halo. */
+int mk_conv2d_wgrad_halo_ups(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
+                             int ldy, float* dwpack_ups, void* stream);
+int mk_conv2d_wgrad_halo_ups_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
+                                int ldy, float* dwpack_ups, void* stream);
+int mk_unpack_wgrad_ups(const float* dwpack_ups, int Co, int Ci, const int* cin_inv, int Cin_p, int Cout_p, float* dw,
+                        int accumulate, void* stream);
 /* dry run: out[16] = co tiles, ci groups, pixel splits, smem bytes, stages, tile rows, ci chunks per CTA, dY boxes, TMEM
  * columns, tiles, tiles per split, UMMA N, stage bytes, x3, valid tile width, tile rows of the image */
 int mk_conv2d_wgrad_halo_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int R, int S, int pad, int x3, int* out);

@@ -545,3 +545,44 @@ MK_EXPORT int mk_unpack_wgrad_acc(const float* dwpack, int Co, int Cig, int R, i
         dwpack, Co, Cig, R, S, groups, cin_inv, Cin_p, Cout_p, grad, total);
     return mk_check_launch("mk_unpack_wgrad_acc");
 }
+
+// Adjoint of the sub-pixel weight pack (mode 4): folds the gradient of the 16 (parity, 2x2 tap) kernels,
+// dwpack_ups [16][Cin_p][Cout_p] from mk_conv2d_wgrad_halo_ups, back onto the 3x3 taps of the parameter.  Tap row r of
+// the 3x3 kernel belongs to sub-row r2 = (r >= 1) for py = 0 ({0} | {1,2}) and r2 = (r >= 2) for py = 1 ({0,1} | {2}).
+template <bool ACC>
+__global__ void k_unpack_wgrad_ups(const float* __restrict__ dwp, int Co, int Ci, const int* __restrict__ cin_inv,
+                                   int Cin_p, int Cout_p, float* __restrict__ dw, long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int s = (int)(i % 3);
+    long long t = i / 3;
+    const int r = (int)(t % 3);
+    t /= 3;
+    const int ci = (int)(t % Ci), co = (int)(t / Ci);
+    const int ci_p = cin_inv ? cin_inv[ci] : ci;
+    float v = 0.f;
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+        const int r2 = py == 0 ? (r >= 1) : (r >= 2);
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+            const int s2 = px == 0 ? (s >= 1) : (s >= 2);
+            const int slot = (py * 2 + px) * 4 + r2 * 2 + s2;
+            v += dwp[((long long)slot * Cin_p + ci_p) * Cout_p + co];
+        }
+    }
+    if (ACC) dw[i] += v; else dw[i] = v;
+}
+
+MK_EXPORT int mk_unpack_wgrad_ups(const float* dwpack_ups, int Co, int Ci, const int* cin_inv, int Cin_p, int Cout_p,
+                                  float* dw, int accumulate, void* stream) {
+    long long total = (long long)Co * Ci * 9;
+    if (total == 0) return 0;
+    if (accumulate)
+        k_unpack_wgrad_ups<true><<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            dwpack_ups, Co, Ci, cin_inv, Cin_p, Cout_p, dw, total);
+    else
+        k_unpack_wgrad_ups<false><<<(unsigned)mk_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            dwpack_ups, Co, Ci, cin_inv, Cin_p, Cout_p, dw, total);
+    return mk_check_launch("mk_unpack_wgrad_ups");
+}

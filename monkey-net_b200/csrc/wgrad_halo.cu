@@ -22,7 +22,13 @@
 //   * accumulates in TMEM across ALL pixel tiles of the CTA's range ((chunks x S) accumulators of co columns), one
 //     epilogue at the end: lane quarter q of the accumulator = tap row q, written (pixel splits: fp32 atomics) to the
 //     packed gradient [tap][Cin_p][Cout_p].
-// Grid = (co tiles, ci-chunk groups, pixel splits).  Envelope: stride 1, R = S in {3, 4}, image at least one tile.
+//   * UPSAMPLED CONV (mk_conv2d_wgrad_halo_ups): the weight gradient of conv3x3(nearest_x2(x)) is taken on the LOW-resolution
+//     grid as four sub-pixel passes (output parity py, px): dWsub[parity][2x2 tap] = sum dY[2h+py][2w+px] X[h + r2 - (1-py)]
+//     [w + s2 - (1-px)] - the X halo is the low-resolution tensor itself (no upsampled copy), dY is read through a 5-D
+//     TMA map (c, px, w, py, n*H + h), and mk_unpack_wgrad_ups folds the 16 sub-kernels back onto the 3x3 taps (the
+//     adjoint of the sub-pixel weight pack).  16 tap-pixel products per low-res pixel instead of 36.
+// Grid = (co tiles, ci-chunk groups, pixel splits).  Envelope: stride 1, R = S in {3, 4} (2: sub-pixel passes), image at
+// least one tile.
 #include "common.cuh"
 #include "../../include/monkey_b200.h"
 #include "tc_common.cuh"
@@ -35,7 +41,8 @@ constexpr int WH_SMEM_MAX = 227 * 1024;
 constexpr int WH_MAXST = 4;
 
 struct WHP {
-    int N, Ho, Wo, Cout_p, Cin_p, R, S, pad;
+    int N, Ho, Wo, Cout_p, Cin_p, R, S, pad_h, pad_w;
+    int ups, py, px;             // sub-pixel pass: dY parity (py, px), X = the low-resolution input
     int TR, TWv, tilesW, tilesH, ntiles, tiles_per_split;
     int xa_half, dy_half;        // bytes of one ci-chunk halo / one 32-channel dY box (hi halves)
     int nci, nco, co_pad;        // ci chunks per CTA, dY boxes per CTA, UMMA N
@@ -139,10 +146,11 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 uint8_t* sb = smem + st * p.stage_bytes;
                 mbar_expect_tx(&full[st], nci * p.xa_half + nco * p.dy_half);
                 for (int c = 0; c < nci; ++c)
-                    tma_load_4d(sb + c * p.xa_half, &tmX, &full[st], (ci_chunk0 + c) * 32, w0 - p.pad, h0 - p.pad, n);
+                    tma_load_4d(sb + c * p.xa_half, &tmX, &full[st], (ci_chunk0 + c) * 32, w0 - p.pad_w, h0 - p.pad_h, n);
                 uint8_t* dyb = sb + (p.x_region << (X3 ? 1 : 0));
                 for (int j = 0; j < nco; ++j)
-                    tma_load_4d(dyb + j * p.dy_half, &tmDy, &full[st], co0 + j * 32, w0, h0, n);
+                    if (p.ups) tma_load_5d(dyb + j * p.dy_half, &tmDy, &full[st], co0 + j * 32, p.px, w0, p.py, n * p.Ho + h0);
+                    else tma_load_4d(dyb + j * p.dy_half, &tmDy, &full[st], co0 + j * 32, w0, h0, n);
                 if (++st == p.stages) { st = 0; ph ^= 1; }
             }
         }
@@ -297,17 +305,26 @@ k_wgrad_halo(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 static thread_local int t_whx3 = 0;
 static thread_local int* t_whplan = nullptr;
 
+static thread_local int t_whups = -1;   // >= 0: sub-pixel pass (parity py * 2 + px) of the upsampled conv's weight gradient
+
 // Returns 0 on success, -2 outside the envelope (callers use mk_conv2d_wgrad_tc).
-MK_EXPORT int mk_conv2d_wgrad_halo(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,
-                                   int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream) {
-    const int Ho = Hin + 2 * pad - R + 1, Wo = Win + 2 * pad - S + 1;
-    if (Cin_p % 4 || Cout_p % 4 || ldx % 4 || ldy % 4 || R != S || (R != 3 && R != 4) || Ho < 1 || Wo < 1) {
+static int wgrad_halo_impl(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,
+                           int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream) {
+    const int ups_par = t_whups;
+    const int Ho = ups_par >= 0 ? Hin : Hin + 2 * pad - R + 1, Wo = ups_par >= 0 ? Win : Win + 2 * pad - S + 1;
+    if (Cin_p % 4 || Cout_p % 4 || ldx % 4 || ldy % 4 || R != S || (R != 3 && R != 4 && !(R == 2 && ups_par >= 0)) ||
+        (ups_par >= 0 && (R != 2 || Hin % 8)) || Ho < 1 || Wo < 1) {
         mk_set_error("mk_conv2d_wgrad_halo: outside the halo kernel's envelope");
         return -2;
     }
     WHP p;
     p.x3 = t_whx3;
-    p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout_p = Cout_p; p.Cin_p = Cin_p; p.R = R; p.S = S; p.pad = pad; p.dw = dwpack;
+    p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout_p = Cout_p; p.Cin_p = Cin_p; p.R = R; p.S = S; p.dw = dwpack;
+    p.ups = ups_par >= 0 ? 1 : 0;
+    p.py = p.ups ? (ups_par >> 1) : 0;
+    p.px = p.ups ? (ups_par & 1) : 0;
+    p.pad_h = p.ups ? 1 - p.py : pad;
+    p.pad_w = p.ups ? 1 - p.px : pad;
     p.TWv = 16 - (S - 1);
     p.tilesW = (Wo + p.TWv - 1) / p.TWv;
     p.total_chunks = (Cin_p + 31) / 32;
@@ -384,7 +401,18 @@ MK_EXPORT int mk_conv2d_wgrad_halo(const float* x, int N, int Hin, int Win, int 
                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         MK_REQUIRE(rc == CUDA_SUCCESS, "mk_conv2d_wgrad_halo: x tensor map rejected (%d)", (int)rc);
     }
-    {
+    if (p.ups) {
+        // dY[n][2h + py][2w + px][c] as (c, px, w, py, n * H + h): full-resolution strides, low-resolution tile grid
+        cuuint64_t dims[5] = {(cuuint64_t)Cout_p, 2, (cuuint64_t)Wo, 2, (cuuint64_t)N * Ho};
+        cuuint64_t strides[4] = {(cuuint64_t)ldy * 4, (cuuint64_t)2 * ldy * 4, (cuuint64_t)2 * Wo * ldy * 4,
+                                 (cuuint64_t)4 * Wo * ldy * 4};
+        cuuint32_t box[5] = {32, 1, 16, 1, (cuuint32_t)p.TR};
+        cuuint32_t es5[5] = {1, 1, 1, 1, 1};
+        CUresult rc = encode(&tmDy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(dy), dims, strides, box, es5,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        MK_REQUIRE(rc == CUDA_SUCCESS, "mk_conv2d_wgrad_halo: sub-pixel dy tensor map rejected (%d)", (int)rc);
+    } else {
         cuuint64_t dims[4] = {(cuuint64_t)Cout_p, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)Wo * ldy * 4, (cuuint64_t)Ho * Wo * ldy * 4};
         cuuint32_t box[4] = {32, 16, (cuuint32_t)p.TR, 1};
@@ -412,6 +440,9 @@ MK_EXPORT int mk_conv2d_wgrad_halo(const float* x, int N, int Hin, int Win, int 
     if (S == 3) {
         if (p.TR == 8) { if (p.x3) WH_LAUNCH(3, 8, true); else WH_LAUNCH(3, 8, false); }
         else { if (p.x3) WH_LAUNCH(3, 4, true); else WH_LAUNCH(3, 4, false); }
+    } else if (S == 2) {
+        if (p.TR == 8) { if (p.x3) WH_LAUNCH(2, 8, true); else WH_LAUNCH(2, 8, false); }
+        else { if (p.x3) WH_LAUNCH(2, 4, true); else WH_LAUNCH(2, 4, false); }
     } else {
         if (p.TR == 8) { if (p.x3) WH_LAUNCH(4, 8, true); else WH_LAUNCH(4, 8, false); }
         else { if (p.x3) WH_LAUNCH(4, 4, true); else WH_LAUNCH(4, 4, false); }
@@ -419,6 +450,39 @@ MK_EXPORT int mk_conv2d_wgrad_halo(const float* x, int N, int Hin, int Win, int 
 #undef WH_LAUNCH
     if (le != cudaSuccess) { mk_set_error("mk_conv2d_wgrad_halo: smem attribute: %s", cudaGetErrorString(le)); return (int)le; }
     return mk_check_launch("mk_conv2d_wgrad_halo");
+}
+
+MK_EXPORT int mk_conv2d_wgrad_halo(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,
+                                   int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream) {
+    t_whups = -1;
+    return wgrad_halo_impl(x, N, Hin, Win, Cin_p, ldx, dy, Cout_p, ldy, R, S, pad, dwpack, stream);
+}
+
+// Weight gradient of conv3x3(nearest_x2(x)), pad 1, on the low-resolution grid: x [N][Hin][Win][ldx] (NOT upsampled),
+// dy [N][2 Hin][2 Win][ldy]; dwpack_ups [16 = parity x 2x2 tap][Cin_p][Cout_p] (the gradient of the mode-4 pack; fold it
+// onto the 3x3 taps with mk_unpack_wgrad_ups).  -2 (nothing launched) outside the envelope.
+MK_EXPORT int mk_conv2d_wgrad_halo_ups(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,
+                                       int Cout_p, int ldy, float* dwpack_ups, void* stream) {
+    int rc = 0;
+    for (int par = 0; par < 4 && rc == 0; ++par) {
+        t_whups = par;
+        rc = wgrad_halo_impl(x, N, Hin, Win, Cin_p, ldx, dy, Cout_p, ldy, 2, 2, 0,
+                             dwpack_ups + (size_t)par * 4 * Cin_p * Cout_p, stream);
+        if (rc == -2 && par > 0) {
+            mk_set_error("mk_conv2d_wgrad_halo_ups: parity %d refused after parity 0 was launched", par);
+            rc = -1;
+        }
+    }
+    t_whups = -1;
+    return rc;
+}
+
+MK_EXPORT int mk_conv2d_wgrad_halo_ups_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,
+                                          int Cout_p, int ldy, float* dwpack_ups, void* stream) {
+    t_whx3 = 1;
+    const int rc = mk_conv2d_wgrad_halo_ups(x, N, Hin, Win, Cin_p, ldx, dy, Cout_p, ldy, dwpack_ups, stream);
+    t_whx3 = 0;
+    return rc;
 }
 
 MK_EXPORT int mk_conv2d_wgrad_halo_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy,

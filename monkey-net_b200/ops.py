@@ -374,7 +374,22 @@ class _Conv(torch.autograd.Function):
             else:
                 lib.call('mk_conv2d', dy.data_ptr(), N, dy.shape[1], dy.shape[2], Cop, Cop, 0, wt.data_ptr(), R, S,
                          R - 1 - pad, None, None, None, 0, 0, 0.0, dx.data_ptr(), Cp, Cp, 2 if ups else 0, st)
-        if ctx.needs_input_grad[1]:
+        ups_done = False
+        if (ctx.needs_input_grad[1] and tc and ups and CONV_HALO and CONV_HALO_UPS and R == 3 and S == 3 and pad == 1
+                and groups == 1):
+            # upsampled conv: the weight gradient on the low-resolution grid (four sub-pixel passes, no upsampled copy
+            # of x), folded onto the 3x3 taps by the adjoint of the sub-pixel pack
+            dwp16 = _empty(16 * Cp * Cop, like=x)
+            rc = lib.call_soft('mk_conv2d_wgrad_halo_ups_x3' if x3 else 'mk_conv2d_wgrad_halo_ups', (-2,), x.data_ptr(), N,
+                               Hin, Win, Cp, Cp, dy.data_ptr(), Cop, Cop, dwp16.data_ptr(), st)
+            if rc == 0:
+                tgt = _direct_grad_target(weight)
+                if tgt is None:
+                    dw = torch.empty_like(weight)
+                lib.call('mk_unpack_wgrad_ups', dwp16.data_ptr(), Co, Cig, _ptr(cinv), Cp, Cop,
+                         (tgt if tgt is not None else dw).data_ptr(), 1 if tgt is not None else 0, st)
+                ups_done = True
+        if ctx.needs_input_grad[1] and not ups_done:
             dwp = _empty(R * S * Cp * Cop, like=x)
             if tc:
                 xin = x

@@ -165,6 +165,38 @@ def test_conv_upsampled_halo_declines_ragged_heights():
     assert rc == -2 and float(y.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('x3', [False, True])
+@pytest.mark.parametrize('cin,cout,H,W,N', [(128, 32, 64, 64, 4), (140, 32, 32, 32, 4), (64, 64, 32, 48, 4),
+                                             (36, 12, 64, 64, 2), (256, 160, 32, 32, 4), (20, 48, 32, 32, 2)])
+def test_wgrad_upsampled_halo_matches_torch_autograd(cin, cout, H, W, N, x3):
+    """mk_conv2d_wgrad_halo_ups + mk_unpack_wgrad_ups: d/dw of conv3x3(nearest_x2(x)) taken on the low-resolution grid
+    (four sub-pixel passes, dY through a 5-D TMA map, adjoint of the sub-pixel pack) == torch autograd in double."""
+    from monkey_net_b200 import lib
+    torch.manual_seed(cin * 3 + cout)
+    dev = torch.device('cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(N, H, W, cin, device=dev)
+    dy = torch.randn(N, 2 * H, 2 * W, cout, device=dev)
+    dwp = torch.full((16 * cin * cout,), float('nan'), device=dev)
+    rc = lib.call_soft('mk_conv2d_wgrad_halo_ups_x3' if x3 else 'mk_conv2d_wgrad_halo_ups', (-2,), x.data_ptr(), N, H, W,
+                       cin, cin, dy.data_ptr(), cout, cout, dwp.data_ptr(), st)
+    assert rc == 0, 'declined'
+    dw = torch.empty(cout, cin, 1, 3, 3, device=dev)
+    lib.call('mk_unpack_wgrad_ups', dwp.data_ptr(), cout, cin, None, cin, cout, dw.data_ptr(), 0, st)
+    torch.cuda.synchronize()
+    wd = torch.zeros(cout, cin, 3, 3, dtype=torch.double, device=dev, requires_grad=True)
+    xu = torch.nn.functional.interpolate(x.double().permute(0, 3, 1, 2), scale_factor=2, mode='nearest')
+    out = torch.nn.functional.conv2d(xu, wd, padding=1)
+    gw, = torch.autograd.grad(out, wd, dy.double().permute(0, 3, 1, 2))
+    err = float((dw[:, :, 0].double() - gw).abs().max()) / (float(gw.abs().max()) + 1e-12)
+    assert err < KERNEL_TOL['tf32x3' if x3 else 'tf32'] * (2 if x3 else 1), err
+    # accumulate flag: += into the destination
+    dw2 = dw.clone()
+    lib.call('mk_unpack_wgrad_ups', dwp.data_ptr(), cout, cin, None, cin, cout, dw2.data_ptr(), 1, st)
+    torch.cuda.synchronize()
+    assert torch.allclose(dw2, 2 * dw, rtol=1e-6, atol=0)
+
+
 WGRAD_CASES = [(32, 64, 3, 1, 16, 16, 4), (64, 128, 3, 1, 32, 32, 2),
                (16, 32, 3, 1, 64, 64, 2), (48, 144, 3, 1, 13, 9, 3),
                (256, 256, 3, 1, 4, 4, 8), (512, 128, 3, 1, 2, 2, 32),

@@ -19,10 +19,13 @@ import yaml  # noqa: E402
 
 CONV = ('mk_conv2d', 'mk_conv2d_wgrad', 'mk_conv2d_tc', 'mk_conv2d_wgrad_tc', 'mk_conv2d_tc_x3', 'mk_conv2d_wgrad_tc_x3',
         'mk_conv2d_tc_halo', 'mk_conv2d_tc_halo_x3', 'mk_conv2d_wgrad_halo', 'mk_conv2d_wgrad_halo_x3',
-        'mk_conv2d_tc_halo_ups', 'mk_conv2d_tc_halo_ups_x3')
+        'mk_conv2d_tc_halo_ups', 'mk_conv2d_tc_halo_ups_x3', 'mk_conv2d_wgrad_halo_ups', 'mk_conv2d_wgrad_halo_ups_x3')
 
 
 def signature(name, a):
+    if name in ('mk_conv2d_wgrad_halo_ups', 'mk_conv2d_wgrad_halo_ups_x3'):
+        N, H, W, Ci, Co = a[1], a[2], a[3], a[4], a[7]
+        return 'N%d %dx%d ci%d co%d k3 p1 ups' % (N, H, W, Ci, Co), 2.0 * N * 4 * H * W * Ci * Co * 9
     if name in ('mk_conv2d_tc_halo_ups', 'mk_conv2d_tc_halo_ups_x3'):
         N, H, W, Ci, Co = a[1], a[2], a[3], a[4], a[12]
         return 'N%d %dx%d ci%d co%d k3 p1 ups' % (N, H, W, Ci, Co), 2.0 * N * 4 * H * W * Ci * Co * 9

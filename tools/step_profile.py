@@ -24,7 +24,8 @@ KERNEL_OF = {'mk_conv2d_tc': 'k_conv_tc', 'mk_conv2d_wgrad_tc': 'k_wgrad_tc', 'm
              'mk_conv2d_wgrad': 'k_conv_wgrad', 'mk_conv2d_tc_x3': 'k_conv_tc', 'mk_conv2d_wgrad_tc_x3': 'k_wgrad_tc',
              'mk_conv2d_tc_halo': 'k_conv_halo', 'mk_conv2d_tc_halo_x3': 'k_conv_halo',
              'mk_conv2d_wgrad_halo': 'k_wgrad_halo', 'mk_conv2d_wgrad_halo_x3': 'k_wgrad_halo',
-             'mk_conv2d_tc_halo_ups': 'k_conv_halo', 'mk_conv2d_tc_halo_ups_x3': 'k_conv_halo'}
+             'mk_conv2d_tc_halo_ups': 'k_conv_halo', 'mk_conv2d_tc_halo_ups_x3': 'k_conv_halo',
+             'mk_conv2d_wgrad_halo_ups': 'k_wgrad_halo', 'mk_conv2d_wgrad_halo_ups_x3': 'k_wgrad_halo'}
 
 
 def short(name):
