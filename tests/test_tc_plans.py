@@ -123,3 +123,26 @@ def test_every_layer_has_a_valid_tensor_core_plan(name, res, batch):
             assert gy * taps >= k * k and gz <= 65535
             n_layers += 1
     assert n_layers > 40
+
+
+def test_wgrad_pixel_splits_fill_whole_waves():
+    """tc_common.cuh:pick_splits - the weight-gradient kernels split their pixel range so that the CTAs form whole waves of
+    the 148 SMs: ceil(148 / groups) splits used to overshoot one wave (16 groups x 10 = 160 CTAs = two waves of 64 tiles
+    where one wave of 72 does; measured 795 -> 447 us on 512->128 @64x64 x 16)."""
+    from monkey_net_b200 import lib as mklib
+    lib = mklib.load()
+    for N, H, W, ci, co, k, pad in [(16, 64, 64, 512, 128, 3, 1), (8, 61, 61, 128, 256, 4, 0), (16, 32, 32, 256, 512, 3, 1),
+                                    (8, 256, 256, 48, 48, 3, 1), (16, 256, 256, 128, 32, 3, 1)]:
+        rc, o = plan(lib, 'mk_conv2d_wgrad_halo_plan', N, H, W, ci, co, k, k, pad, 1)
+        assert rc == 0
+        cot, cig, spl, _, _, _, _, _, _, ntiles, tps = o[:11]
+        ctas = cot * cig * spl
+        waves = -(-ctas // 148)
+        # no split count with fewer waves x tiles-per-CTA exists among the neighbours (+ the per-CTA epilogue of ~6 tiles)
+        cost = waves * (tps + 6)
+        for alt in range(1, min(ntiles, 4 * 148 // (cot * cig) + 1) + 1):
+            a_tps = -(-ntiles // alt)
+            a_eff = -(-ntiles // a_tps)
+            a_cost = -(-(cot * cig * a_eff) // 148) * (a_tps + 6)
+            assert cost <= a_cost * 1.001, (N, H, W, ci, co, spl, alt)
+        assert tps * spl >= ntiles and tps * (spl - 1) < ntiles
