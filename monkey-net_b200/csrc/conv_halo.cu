@@ -88,21 +88,6 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// tcgen05.mma with the two operand descriptors given as their low words (start address | LBO) + the shared high word
-__device__ __forceinline__ void umma_lh(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
-                                        uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
-        ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
-constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
-
 // One chunk's MMAs for one row-block with RESIDENT weights, fully unrolled over taps and K steps (NK compile-time):
 // per MMA two 64-bit uniform adds + one UTCHMMA, no predicates, no loop-carried vector registers.
 template <int R, int S, bool X3, int NK, int RBT, bool CT>
