@@ -146,3 +146,24 @@ def test_wgrad_pixel_splits_fill_whole_waves():
             a_cost = -(-(cot * cig * a_eff) // 148) * (a_tps + 6)
             assert cost <= a_cost * 1.001, (N, H, W, ci, co, spl, alt)
         assert tps * spl >= ntiles and tps * (spl - 1) < ntiles
+
+
+def test_column_taps_on_n_is_chosen_where_the_mma_phase_dominates():
+    """conv_halo.cu:halo_wants_ct through the planner's flag (bit 3 of out[15]): narrow layers with many K steps stack their
+    column taps on N, layers whose epilogue dominates (few input channels, or many output groups) keep the plain schedule,
+    and a CT plan that does not fit shared memory falls back instead of failing."""
+    from monkey_net_b200 import lib as mklib
+    lib = mklib.load()
+
+    def ct(N, H, W, ci, k, pad, co, res, x3):
+        rc, o = plan(lib, 'mk_conv2d_tc_halo_plan', N, H, W, ci, k, k, pad, co, res, x3)
+        assert rc == 0, lib.mk_last_error()
+        return (o[15] >> 3) & 1, o
+    assert ct(8, 256, 256, 128, 3, 1, 32, 0, 0)[0] == 1      # 128->32: 16 K steps per tap
+    assert ct(8, 253, 253, 64, 4, 3, 16, 0, 0)[0] == 1       # 64->16 4x4 (dgrad of the discriminator's first block)
+    assert ct(8, 256, 256, 48, 3, 1, 48, 0, 1)[0] == 1       # 48->48 in reference precision (2 MMAs per K step)
+    assert ct(16, 256, 256, 4, 3, 1, 64, 0, 0)[0] == 0       # image input: one K step, two output groups
+    assert ct(8, 256, 256, 32, 3, 1, 128, 0, 0)[0] == 0      # S * Cout > 256: not eligible
+    assert ct(8, 256, 256, 36, 3, 1, 12, 0, 0)[0] == 0       # Cout_p % 16 != 0: TMEM column groups would be unaligned
+    flag, o = ct(8, 256, 256, 16, 4, 0, 64, 0, 1)            # N = 256 in reference precision: no shared-memory plan -> plain
+    assert flag == 0 and o[2] in (1, 2, 4)
