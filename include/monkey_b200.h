@@ -136,6 +136,7 @@ int mk_conv2d_tc_halo_ups_x3(const float* x, int N, int Hin, int Win, int Cin_p,
  * columns, tiles, halo rows, halo stage bytes, weight slot bytes, valid tile width, output groups, acc columns, x3 */
 int mk_conv2d_tc_halo_plan(int N, int Hin, int Win, int Cin_p, int R, int S, int pad, int Cout_p, int has_resid, int x3,
                            int* out);
+int mk_conv2d_tc_halo_ups_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int x3, int* out /* host, 16 ints */);
 /* dwpack[R*S][Cin_p][Cout_p] = sum over pixels of im2col(x)^T dy  (zero-filled inside). */
 int mk_conv2d_wgrad(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, int ups,
                     const float* dy, int Cout_p, int ldy, int R, int S, int pad, float* dwpack, void* stream);
@@ -169,6 +170,7 @@ int mk_unpack_wgrad_ups(const float* dwpack_ups, int Co, int Ci, const int* cin_
 /* dry run: out[16] = co tiles, ci groups, pixel splits, smem bytes, stages, tile rows, ci chunks per CTA, dY boxes, TMEM
  * columns, tiles, tiles per split, UMMA N, stage bytes, x3, valid tile width, tile rows of the image */
 int mk_conv2d_wgrad_halo_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int R, int S, int pad, int x3, int* out);
+int mk_conv2d_wgrad_halo_ups_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int x3, int* out /* host, 16 ints */);
 /* 3xTF32 variant (see mk_conv2d_tc_x3): both operand tiles are split hi + lo in shared memory. */
 int mk_conv2d_wgrad_tc_x3(const float* x, int N, int Hin, int Win, int Cin_p, int ldx, const float* dy, int Cout_p,
                           int ldy, int R, int S, int pad, float* dwpack, void* stream);

@@ -862,3 +862,15 @@ MK_EXPORT int mk_conv2d_tc_halo_plan(int N, int Hin, int Win, int Cin_p, int R, 
     t_hx3 = 0;
     return rc;
 }
+
+// Dry run of the four sub-pixel passes of the upsampled conv (they share one plan): same out[16] as above.
+MK_EXPORT int mk_conv2d_tc_halo_ups_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int x3, int* out) {
+    MK_REQUIRE(out != nullptr, "mk_conv2d_tc_halo_ups_plan: out is NULL");
+    t_hplan = out;
+    t_hx3 = x3 ? 1 : 0;
+    const int rc = mk_conv2d_tc_halo_ups(nullptr, N, Hin, Win, Cin_p, Cin_p, nullptr, nullptr, nullptr, 0, 0.f, nullptr,
+                                         Cout_p, Cout_p, nullptr);
+    t_hplan = nullptr;
+    t_hx3 = 0;
+    return rc;
+}

@@ -506,3 +506,14 @@ MK_EXPORT int mk_conv2d_wgrad_halo_plan(int N, int Hin, int Win, int Cin_p, int 
     t_whx3 = 0;
     return rc;
 }
+
+// Dry run of the four sub-pixel passes of the upsampled conv's weight gradient: same out[16] as above.
+MK_EXPORT int mk_conv2d_wgrad_halo_ups_plan(int N, int Hin, int Win, int Cin_p, int Cout_p, int x3, int* out) {
+    MK_REQUIRE(out != nullptr, "mk_conv2d_wgrad_halo_ups_plan: out is NULL");
+    t_whplan = out;
+    t_whx3 = x3 ? 1 : 0;
+    const int rc = mk_conv2d_wgrad_halo_ups(nullptr, N, Hin, Win, Cin_p, Cin_p, nullptr, Cout_p, Cout_p, nullptr, nullptr);
+    t_whplan = nullptr;
+    t_whx3 = 0;
+    return rc;
+}

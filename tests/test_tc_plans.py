@@ -106,6 +106,25 @@ def test_every_layer_has_a_valid_tensor_core_plan(name, res, batch):
                         assert gx * gy <= 148 and ntiles >= gx and (fl & 1) == x3 and ((fl >> 1) & 3) in (1, 2, 3)
                         nstg = (fl >> 1) & 3
                         assert a_st * a_stage + b_sl * b_slot + nstg * (1 + res_) * twv * 8 * 128 + 3072 == smem
+                if k == 3 and groups == 1 and H % 2 == 0 and W % 2 == 0:
+                    # the upsampled conv on the halo kernels: four sub-pixel passes on the low-resolution grid (forward:
+                    # 2x2 halo conv + 5-D store map; weight gradient: 2x2 taps, dY through a 5-D load map)
+                    rc, o = plan(lib, 'mk_conv2d_tc_halo_ups_plan', N, H // 2, W // 2, cin_p, cop, x3)
+                    assert rc in (0, -2), (name, 'halo ups', lib.mk_last_error())
+                    if rc == 0:
+                        gx, gy, rb, smem, a_st, b_sl, resident, tmem, ntiles, halo_rows, a_stage, b_slot, twv, ngr, npad, fl = o
+                        assert smem <= 227 * 1024 and 2 <= a_st <= 4 and rb in (1, 2, 4) and (H // 2) % (8 * rb) == 0
+                        assert halo_rows == 8 * rb + 2 and twv == 15 and 2 * rb * npad <= tmem <= 512
+                        assert gx * gy <= 148 and ntiles >= gx and (fl & 1) == x3
+                        nstg = (fl >> 1) & 3
+                        assert a_st * a_stage + b_sl * b_slot + nstg * twv * 8 * 128 + 3072 == smem
+                    rc, o = plan(lib, 'mk_conv2d_wgrad_halo_ups_plan', N, H // 2, W // 2, cin_p, cop, x3)
+                    assert rc in (0, -2), (name, 'wgrad halo ups', lib.mk_last_error())
+                    if rc == 0:
+                        cot, cig, spl, smem, stages, tr, nci, nco, tmem, ntiles, tps, co_pad, stage, f3, twv, tilesh = o
+                        assert smem <= 227 * 1024 and 2 <= stages <= 4 and tr in (4, 8) and (H // 2) % tr == 0 and twv == 15
+                        assert nci * 2 * co_pad <= tmem <= 512 and cig * nci >= (cin_p + 31) // 32
+                        assert tps * spl >= ntiles and tps * (spl - 1) < ntiles and spl <= 65535
                 rc, o = plan(lib, 'mk_conv2d_wgrad_halo_plan', N, H, W, cin_p, cop, k, k, pad, x3)
                 assert rc in (0, -2), (name, 'wgrad halo', lib.mk_last_error())
                 if rc == 0:
